@@ -1,0 +1,66 @@
+// api_host.cpp — extern "C" wrappers of the host plumbing (scene load, BVH, accessors).
+// Errors: the reference THROWs std::string and exits from main (src/Exceptions.h:28-33,
+// src/renderer.cc:637-640); here every failure becomes a negative status + b200r_last_error() text.
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+
+#include "scene.h"
+
+namespace b200r {
+static std::mutex g_err_mu;
+static std::string g_last_error;
+void set_global_error(const std::string& s) { std::lock_guard<std::mutex> l(g_err_mu); g_last_error = s; }
+const char* global_error() { return g_last_error.c_str(); }
+}  // namespace b200r
+
+struct b200r_scene { b200r::Scene s; };
+
+extern "C" {
+
+const char* b200r_version(void) { return "renderer_b200 0.1 (sm_100a)"; }
+
+int b200r_scene_load(const char* filename, b200r_scene** out)
+{
+    if (!filename || !out) { b200r::set_global_error("b200r_scene_load: NULL argument"); return B200R_EINVAL; }
+    *out = nullptr;
+    b200r_scene* h = nullptr;
+    try {
+        h = new b200r_scene();
+        h->s.load(filename);
+        if (h->s.tris.empty()) throw std::runtime_error(std::string("no triangles in ") + filename);
+    } catch (const std::exception& e) {
+        delete h;
+        b200r::set_global_error(e.what());
+        return B200R_EIO;
+    }
+    *out = h;
+    return B200R_OK;
+}
+
+void b200r_scene_free(b200r_scene* s) { delete s; }
+
+int b200r_scene_build_bvh(b200r_scene* s, const char* cache_path, int force_rebuild)
+{
+    if (!s) { b200r::set_global_error("b200r_scene_build_bvh: NULL scene"); return B200R_EINVAL; }
+    try {
+        s->s.build_bvh(cache_path, force_rebuild != 0);
+    } catch (const std::exception& e) {
+        b200r::set_global_error(e.what());
+        return B200R_EDEPTH;
+    }
+    return B200R_OK;
+}
+
+const b200r_vertex* b200r_scene_vertices(const b200r_scene* s, uint32_t* n)
+{ if (n) *n = (uint32_t)s->s.verts.size(); return s->s.verts.data(); }
+const b200r_tri* b200r_scene_tris(const b200r_scene* s, uint32_t* n)
+{ if (n) *n = (uint32_t)s->s.tris.size(); return s->s.tris.data(); }
+const b200r_bvhnode* b200r_scene_nodes(const b200r_scene* s, uint32_t* n)
+{ if (n) *n = (uint32_t)s->s.nodes.size(); return s->s.nodes.data(); }
+const int32_t* b200r_scene_tri_idx(const b200r_scene* s, uint32_t* n)
+{ if (n) *n = (uint32_t)s->s.tri_idx.size(); return s->s.tri_idx.data(); }
+int b200r_scene_bvh_depth(const b200r_scene* s) { return s->s.bvh_depth; }
+
+}  // extern "C"
