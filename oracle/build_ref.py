@@ -134,6 +134,8 @@ def build(a):
             # the single permitted semantic delta: seed the per-pixel random stream
             sub_exact(rt, r"^(\s*for\(int x=xStarting; x<iOnePastEndingX; x\+\+\) \{)\s*$",
                       r"\1 oracle_seed(x, y);")
+            # ... and draw from it instead of the process-global, racy libc rand() (3 call sites, :393-395)
+            sub_exact(rt, r"float\(rand\(\)-RAND_MAX/2\)", "float(oracle_rand()-RAND_MAX/2)", count=3)
 
         flags = FAST_FLAGS if a.fast else STRICT_FLAGS
         inc = ["-I", work, "-I", STUB, "-I", os.path.join(REF, "lib3ds-1.3.0")]
@@ -144,7 +146,7 @@ def build(a):
             for u in units:
                 o = os.path.join(work, u + ".o")
                 objs.append(o)
-                extra = ["-Drand=oracle_rand"] if (a.ao and u == "Raytracer") else []
+                extra = []
                 futs.append(ex.submit(run, ["g++", "-std=gnu++14"] + flags + extra + inc +
                                       ["-c", os.path.join(src, u + ".cc"), "-o", o]))
             o = os.path.join(work, "sdl_stub.o")

@@ -45,3 +45,7 @@ int oracle_render(const oracle_scene* s, const b200r_frame* f, uint32_t* out, b2
 }
 
 }  // extern "C"
+
+// (raster / shadow-map / MLAA restatements live in raster_port.cpp / mlaa_port.cpp)
+extern "C" __attribute__((weak)) int oracle_render_shadowmap(const oracle_scene*, const float*, const float*, float*) { return -3; }
+extern "C" __attribute__((weak)) int oracle_mlaa(uint32_t*, int, int) { return -3; }

@@ -1,0 +1,291 @@
+"""renderer_b200 — thin Python binding over the C-ABI of libb200render.so (include/b200render.h).
+
+The product is the shared library (C++ host plumbing + hand-written sm_100a CUDA kernels); this
+module only loads it with ctypes so that tests and bench.py can drive it. Names follow the
+reference's domain (Scene / Camera / Light / Screen and the Scene::render* entry points of
+reference src/Scene.h:76-85). There is no Python or CPU rendering fallback: if the library is
+missing, importing works but every use raises; if there is no B200, Renderer() raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from ._abi import (F_AO, F_DEFAULT, F_MLAA, F_PHONG_NORMAL, F_REFLECTIONS, F_SHADOWS,  # noqa: F401
+                   MODE_AMBIENT, MODE_GOURAUD, MODE_LINES, MODE_PHONG, MODE_PHONG_SHADOWMAPS,
+                   MODE_PHONG_SOFTSHADOWMAPS, MODE_POINTS, MODE_POINTS_TRI, MODE_RAYTRACE,
+                   MODE_RAYTRACE_AA, Counters, Frame)
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libb200render.so")
+_lib = None
+
+
+class RendererError(RuntimeError):
+    """Raised where the reference would THROW(std::string) (src/Exceptions.h:28-33) or exit()."""
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RendererError(
+                f"{LIB_PATH} is missing: run `python -m renderer_b200.build` (or __graft_entry__.build()). "
+                "There is no fallback renderer.")
+        _lib = _abi.bind(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+def _f9(v):
+    return (C.c_float * 9)(*[float(x) for x in v])
+
+
+def _check(rc, ctx=None):
+    if rc != 0:
+        msg = lib().b200r_last_error(ctx)
+        raise RendererError(f"[{rc}] {msg.decode() if msg else 'unknown error'}")
+
+
+class Scene:
+    """Host-side scene = reference `Scene` after load(): vertices, triangles, flattened BVH."""
+
+    def __init__(self, filename=None):
+        self._h = C.c_void_p()
+        self.filename = None
+        if filename is not None:
+            self.load(filename)
+
+    def load(self, filename):
+        """Scene::load (reference src/Loader.cc:85)."""
+        if self._h:
+            lib().b200r_scene_free(self._h)
+            self._h = C.c_void_p()
+        _check(lib().b200r_scene_load(os.fsencode(filename), C.byref(self._h)))
+        self.filename = filename
+        return self
+
+    def UpdateBoundingVolumeHierarchy(self, cache_path=None, forceRecalc=False):
+        """Scene::UpdateBoundingVolumeHierarchy (reference src/Raytracer.cc:720). cache_path is the
+        `<model>.bvh` file (same format as the reference's); None = build in memory only."""
+        _check(lib().b200r_scene_build_bvh(self._h, os.fsencode(cache_path) if cache_path else None,
+                                            1 if forceRecalc else 0))
+        return self
+
+    def _arr(self, fn, ctype):
+        n = C.c_uint32()
+        p = fn(self._h, C.byref(n))
+        if n.value == 0:
+            return np.zeros(0, dtype=np.uint8), 0
+        buf = C.cast(p, C.POINTER(C.c_uint8 * (n.value * C.sizeof(ctype)))).contents
+        return np.frombuffer(buf, dtype=np.uint8), n.value
+
+    @property
+    def n_vertices(self):
+        n = C.c_uint32(); lib().b200r_scene_vertices(self._h, C.byref(n)); return n.value
+
+    @property
+    def n_triangles(self):
+        n = C.c_uint32(); lib().b200r_scene_tris(self._h, C.byref(n)); return n.value
+
+    @property
+    def n_nodes(self):
+        n = C.c_uint32(); lib().b200r_scene_nodes(self._h, C.byref(n)); return n.value
+
+    @property
+    def bvh_depth(self):
+        return lib().b200r_scene_bvh_depth(self._h)
+
+    def raw(self):
+        """(verts_ptr, nv, tris_ptr, nt, nodes_ptr, nn, triidx_ptr, ni) for the oracle / tests."""
+        L = lib()
+        nv, nt, nn, ni = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        v = L.b200r_scene_vertices(self._h, C.byref(nv)); t = L.b200r_scene_tris(self._h, C.byref(nt))
+        n = L.b200r_scene_nodes(self._h, C.byref(nn)); i = L.b200r_scene_tri_idx(self._h, C.byref(ni))
+        return v, nv.value, t, nt.value, n, nn.value, i, ni.value
+
+    def bvh_bytes(self):
+        """The flattened BVH in the reference's .bvh cache layout (Raytracer.cc:747-753)."""
+        nodes, nn = self._arr(lib().b200r_scene_nodes, _abi.BvhNode)
+        idx, ni = self._arr(lib().b200r_scene_tri_idx, C.c_int32)
+        return np.array([nn, ni], dtype=np.uint32).tobytes() + nodes.tobytes() + idx.tobytes()
+
+    def __del__(self):
+        try:
+            if self._h and _lib is not None:
+                _lib.b200r_scene_free(self._h)
+        except Exception:
+            pass
+
+
+class Camera:
+    """reference `Camera` (src/Camera.h:26-58): eye position + row matrix {up, right, forward}."""
+
+    def __init__(self, eye=(4.8, 0.0, 0.0), lookat=(0.0, 0.0, 0.0)):
+        self.eye = (C.c_float * 3)()
+        self.mv = (C.c_float * 9)()
+        self.set(eye, lookat)
+
+    def set(self, eye, lookat):
+        e = _f3(eye)
+        lib().b200r_camera_look_at(e, _f3(lookat), self.mv)
+        C.memmove(self.eye, e, 12)
+        return self
+
+
+class Orbit:
+    """The `-b` benchmark orbit of main() (reference src/renderer.cc:485-496): frame k of the orbit
+    is the camera after k+1 calls of step()."""
+
+    def __init__(self):
+        self._o = _abi.Orbit()
+        lib().b200r_orbit_init(C.byref(self._o))
+
+    def step(self):
+        cam = Camera.__new__(Camera)
+        cam.eye = (C.c_float * 3)(); cam.mv = (C.c_float * 9)()
+        lib().b200r_orbit_step(C.byref(self._o), cam.eye, cam.mv)
+        return cam
+
+    @staticmethod
+    def cameras(frames):
+        """{k: Camera} for the requested orbit frame numbers."""
+        frames = sorted(set(int(k) for k in frames))
+        o, out = Orbit(), {}
+        for k in range(frames[-1] + 1):
+            cam = o.step()
+            if k in frames:
+                out[k] = cam
+        return out
+
+
+def make_frame(mode, width, height, camera, n_lights=1, flags=F_DEFAULT, ao_samples=32, max_depth=3,
+               frame_index=0, row_first=0, row_step=1):
+    """One iteration of main()'s loop for `mode`: camera + default lights + per-mode light matrices."""
+    f = Frame()
+    lib().b200r_frame_defaults(C.byref(f), mode, width, height, camera.eye, camera.mv, n_lights)
+    f.flags = flags; f.ao_samples = ao_samples; f.max_depth = max_depth; f.frame_index = frame_index
+    f.row_first = row_first; f.row_step = row_step
+    return f
+
+
+class Renderer:
+    """Device context: replaces `Screen` + the Scene::render* calls (reference src/Scene.h:76-85)."""
+
+    def __init__(self, device=0):
+        self._ctx = C.c_void_p()
+        _check(lib().b200r_init(int(device), C.byref(self._ctx)))
+        self.scene = None
+
+    def close(self):
+        if self._ctx:
+            lib().b200r_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, scene):
+        _check(lib().b200r_upload_scene_handle(self._ctx, scene._h), self._ctx)
+        self.scene = scene
+        return self
+
+    def upload_shadowmap(self, light, shadowmap):
+        m = np.ascontiguousarray(shadowmap, dtype=np.float32)
+        assert m.shape == (1024, 1024)
+        _check(lib().b200r_upload_shadowmap(self._ctx, light, m.ctypes.data), self._ctx)
+
+    def render_shadowmap(self, light, light_pos):
+        w2l = (C.c_float * 9)()
+        lp = _f3(light_pos)
+        lib().b200r_light_world_to_light(lp, w2l)
+        _check(lib().b200r_render_shadowmap(self._ctx, light, lp, w2l), self._ctx)
+
+    def download_shadowmap(self, light):
+        m = np.empty((1024, 1024), dtype=np.float32)
+        _check(lib().b200r_download_shadowmap(self._ctx, light, m.ctypes.data), self._ctx)
+        return m
+
+    def set_counters(self, enabled):
+        _check(lib().b200r_set_counters(self._ctx, 1 if enabled else 0), self._ctx)
+
+    def counters(self):
+        c = Counters()
+        _check(lib().b200r_get_counters(self._ctx, C.byref(c)), self._ctx)
+        return c.as_dict()
+
+    def last_kernel_ms(self):
+        t, d = C.c_float(), C.c_float()
+        _check(lib().b200r_last_kernel_ms(self._ctx, C.byref(t), C.byref(d)), self._ctx)
+        return t.value, d.value
+
+    def last_launches(self):
+        n = C.c_uint32()
+        _check(lib().b200r_last_launches(self._ctx, C.byref(n)), self._ctx)
+        return n.value
+
+    @staticmethod
+    def rows_of(frame):
+        step = frame.row_step or 1
+        return (frame.height - frame.row_first + step - 1) // step
+
+    def render(self, frame, out=None):
+        """b200r_render: host buffer out (rows x width uint32 0x00RRGGBB), D2H copy included."""
+        rows = self.rows_of(frame)
+        if out is None:
+            out = np.empty((rows, frame.width), dtype=np.uint32)
+        _check(lib().b200r_render(self._ctx, C.byref(frame), out.ctypes.data), self._ctx)
+        return out
+
+    def render_device(self, frame, dev_ptr, stream=None):
+        _check(lib().b200r_render_device(self._ctx, C.byref(frame), C.c_void_p(dev_ptr),
+                                          C.c_void_p(stream) if stream else None), self._ctx)
+
+    def mlaa_device(self, dev_ptr, width, height, stream=None):
+        _check(lib().b200r_mlaa_device(self._ctx, C.c_void_p(dev_ptr), width, height,
+                                        C.c_void_p(stream) if stream else None), self._ctx)
+
+    def deinterleave_device(self, gathered_ptr, frame_ptr, width, height, n_shards, stream=None):
+        _check(lib().b200r_deinterleave_device(self._ctx, C.c_void_p(gathered_ptr), C.c_void_p(frame_ptr), width,
+                                                height, n_shards, C.c_void_p(stream) if stream else None), self._ctx)
+
+    # ---- the reference's entry points, by name (src/Scene.h:76-85) ----
+    def _mode(self, mode, camera, width, height, **kw):
+        return self.render(make_frame(mode, width, height, camera, **kw))
+
+    def renderPoints(self, camera, width, height, asTriangles=True, **kw):
+        return self._mode(MODE_POINTS_TRI if asTriangles else MODE_POINTS, camera, width, height, **kw)
+
+    def renderWireframe(self, camera, width, height, **kw):
+        return self._mode(MODE_LINES, camera, width, height, **kw)
+
+    def renderAmbient(self, camera, width, height, **kw):
+        return self._mode(MODE_AMBIENT, camera, width, height, **kw)
+
+    def renderGouraud(self, camera, width, height, **kw):
+        return self._mode(MODE_GOURAUD, camera, width, height, **kw)
+
+    def renderPhong(self, camera, width, height, **kw):
+        return self._mode(MODE_PHONG, camera, width, height, **kw)
+
+    def renderPhongAndShadowed(self, camera, width, height, **kw):
+        return self._mode(MODE_PHONG_SHADOWMAPS, camera, width, height, **kw)
+
+    def renderPhongAndSoftShadowed(self, camera, width, height, **kw):
+        return self._mode(MODE_PHONG_SOFTSHADOWMAPS, camera, width, height, **kw)
+
+    def renderRaytracer(self, camera, width, height, antiAlias=False, **kw):
+        return self._mode(MODE_RAYTRACE_AA if antiAlias else MODE_RAYTRACE, camera, width, height, **kw)
+
+
+def default_light_pos(index=0):
+    p = (C.c_float * 3)()
+    lib().b200r_default_light_pos(index, p)
+    return tuple(p)

@@ -1,0 +1,371 @@
+// context.cu — the device half of the C-ABI (include/b200render.h): context, scene upload, frame dispatch.
+//
+// b200r_render() stands where main()'s switch(mode) calls scene.renderXxx(sony, canvas)
+// (reference src/renderer.cc:522-583). There is deliberately NO CPU rendering path in this library:
+// if CUDA is unavailable b200r_init() fails and nothing can be rendered.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "device_types.cuh"
+#include "rt_kernels.cuh"
+
+namespace b200r {
+void set_global_error(const std::string& s);
+const char* global_error();
+}
+
+using namespace b200r;
+
+struct b200r_ctx {
+    int device = -1;
+    int numSMs = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+
+    // scene
+    float4 *d_nodes = nullptr, *d_leaftris = nullptr, *d_shade = nullptr, *d_rverts = nullptr, *d_rtris = nullptr;
+    float* d_shadowmap[B200R_MAX_LIGHTS] = {nullptr, nullptr};
+    DeviceScene sc{};
+    bool have_scene = false, have_bvh = false;
+
+    // frame resources
+    uint32_t* d_frame = nullptr; size_t frame_words = 0;
+    uint32_t* h_pinned = nullptr; size_t pinned_words = 0;
+    unsigned* d_tileCounter = nullptr;
+    DeviceCounters* d_ctr = nullptr;
+    bool counting = false;
+    float last_total_ms = 0.f, last_dominant_ms = 0.f;
+    uint32_t last_launches = 0;
+};
+
+namespace {
+
+int fail(b200r_ctx* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg;
+    set_global_error(msg);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(ctx, B200R_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));   \
+    } while (0)
+
+template <class T>
+cudaError_t upload(T** dptr, const std::vector<T>& h, cudaStream_t s)
+{
+    if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
+    if (h.empty()) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void**)dptr, h.size() * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+
+inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+int make_frame_params(b200r_ctx* ctx, const b200r_frame* f, FrameParams& fp)
+{
+    if (!f) return fail(ctx, B200R_EINVAL, "NULL frame");
+    memset(&fp, 0, sizeof fp);
+    fp.mode = f->mode == 0 ? (uint32_t)B200R_MODE_RAYTRACE_AA : f->mode;
+    if (fp.mode < 1 || fp.mode > 10) return fail(ctx, B200R_EINVAL, "mode must be 1..10");
+    if (f->width == 0 || f->height == 0 || f->width > 16384 || f->height > 16384)
+        return fail(ctx, B200R_EINVAL, "width/height out of range");
+    if (f->n_lights < 1 || f->n_lights > B200R_MAX_LIGHTS) return fail(ctx, B200R_EINVAL, "n_lights must be 1 or 2");
+    fp.W = f->width; fp.H = f->height;
+    fp.n_lights = f->n_lights; fp.flags = f->flags; fp.ao_samples = f->ao_samples;
+    fp.max_depth = f->max_depth ? f->max_depth : 3;
+    if (fp.max_depth > 8) return fail(ctx, B200R_EINVAL, "max_depth > 8");
+    if ((fp.flags & B200R_F_AO) && (fp.ao_samples == 0 || fp.ao_samples > 4096))
+        return fail(ctx, B200R_EINVAL, "ao_samples must be 1..4096 when AO is on");
+    fp.frame_index = f->frame_index;
+    fp.row_step = f->row_step ? f->row_step : 1;
+    fp.row_first = f->row_first;
+    if (fp.row_first >= fp.row_step && !(fp.row_step == 1 && fp.row_first == 0))
+        return fail(ctx, B200R_EINVAL, "row_first must be < row_step");
+    fp.n_rows = (fp.H - fp.row_first + fp.row_step - 1) / fp.row_step;
+    memcpy(fp.eye, f->eye, 12); memcpy(fp.mv, f->mv, 36);
+    for (uint32_t i = 0; i < f->n_lights; i++) {
+        memcpy(fp.light_pos[i], f->lights[i].pos, 12);
+        memcpy(fp.light_cam[i], f->lights[i].in_camera, 12);
+        memcpy(fp.cam2light[i], f->lights[i].cam2light, 36);
+    }
+    return B200R_OK;
+}
+
+int ensure_frame(b200r_ctx* ctx, size_t words)
+{
+    if (ctx->frame_words < words) {
+        if (ctx->d_frame) cudaFree(ctx->d_frame);
+        ctx->d_frame = nullptr; ctx->frame_words = 0;
+        CU(cudaMalloc((void**)&ctx->d_frame, words * 4));
+        ctx->frame_words = words;
+    }
+    return B200R_OK;
+}
+
+int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStream_t stream, FrameParams& fp)
+{
+    int rc = make_frame_params(ctx, f, fp);
+    if (rc) return rc;
+    if (!ctx->have_scene) return fail(ctx, B200R_ESTATE, "b200r_render before b200r_upload_scene");
+    if (ctx->counting) CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(DeviceCounters), stream));
+    ctx->last_launches = 0;
+    CU(cudaEventRecord(ctx->ev0, stream));
+    switch (fp.mode) {
+    case B200R_MODE_RAYTRACE:
+    case B200R_MODE_RAYTRACE_AA:
+        if (!ctx->have_bvh) return fail(ctx, B200R_ESTATE, "ray tracing needs a BVH (nodes/tri_idx were not uploaded)");
+        CU(launch_raytrace(ctx->sc, fp, d_out, ctx->d_tileCounter, ctx->d_ctr, ctx->counting, ctx->numSMs, stream));
+        ctx->last_launches += 1;
+        break;
+    default:
+        return fail(ctx, B200R_EINVAL, "render mode not implemented on the device yet");
+    }
+    CU(cudaEventRecord(ctx->ev1, stream));
+    return B200R_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200r_last_error(const b200r_ctx* ctx) { return ctx ? ctx->err.c_str() : global_error(); }
+
+int b200r_init(int device, b200r_ctx** out)
+{
+    b200r_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, B200R_EINVAL, "b200r_init: NULL out");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, B200R_ENODEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                                  " (this library has no CPU rendering path)");
+    if (device < 0 || device >= n) return fail(nullptr, B200R_EINVAL, "device ordinal out of range");
+    cudaDeviceProp p;
+    e = cudaGetDeviceProperties(&p, device);
+    if (e != cudaSuccess) return fail(nullptr, B200R_ECUDA, cudaGetErrorString(e));
+    if (p.major != 10)
+        return fail(nullptr, B200R_ENODEVICE, std::string("device '") + p.name + "' is sm_" + std::to_string(p.major) +
+                                                  std::to_string(p.minor) + "; this build contains sm_100a code only");
+    ctx = new b200r_ctx();
+    ctx->device = device; ctx->numSMs = p.multiProcessorCount;
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&ctx->ev0)); CU(cudaEventCreate(&ctx->ev1));
+    CU(cudaMalloc((void**)&ctx->d_tileCounter, 64));
+    CU(cudaMalloc((void**)&ctx->d_ctr, sizeof(DeviceCounters)));
+    CU(cudaMemset(ctx->d_ctr, 0, sizeof(DeviceCounters)));
+    *out = ctx;
+    return B200R_OK;
+}
+
+void b200r_destroy(b200r_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->d_nodes); cudaFree(ctx->d_leaftris); cudaFree(ctx->d_shade); cudaFree(ctx->d_rverts); cudaFree(ctx->d_rtris);
+    for (int i = 0; i < B200R_MAX_LIGHTS; i++) cudaFree(ctx->d_shadowmap[i]);
+    cudaFree(ctx->d_frame); cudaFree(ctx->d_tileCounter); cudaFree(ctx->d_ctr);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int b200r_upload_scene(b200r_ctx* ctx, const b200r_vertex* verts, uint32_t n_verts, const b200r_tri* tris,
+                       uint32_t n_tris, const b200r_bvhnode* nodes, uint32_t n_nodes, const int32_t* tri_idx,
+                       uint32_t n_tri_idx)
+{
+    if (!ctx) return fail(nullptr, B200R_EINVAL, "NULL ctx");
+    if (!verts || !tris || n_verts == 0 || n_tris == 0) return fail(ctx, B200R_EINVAL, "empty scene");
+    if ((nodes == nullptr) != (tri_idx == nullptr && n_tri_idx == 0) && nodes == nullptr)
+        return fail(ctx, B200R_EINVAL, "nodes and tri_idx must be given together");
+    CU(cudaSetDevice(ctx->device));
+    for (uint32_t i = 0; i < n_tris; i++)
+        if (tris[i].a >= n_verts || tris[i].b >= n_verts || tris[i].c >= n_verts)
+            return fail(ctx, B200R_EINVAL, "triangle vertex index out of range");
+
+    // ---- validate the BVH like CreateCFBVH does (depth < stack size), plus index ranges
+    if (nodes && n_nodes) {
+        std::vector<std::pair<uint32_t, int>> st; st.push_back({0u, 0});
+        size_t visited = 0;
+        while (!st.empty()) {
+            auto [i, d] = st.back(); st.pop_back();
+            if (i >= n_nodes) return fail(ctx, B200R_EINVAL, "BVH child index out of range");
+            if (++visited > n_nodes) return fail(ctx, B200R_EINVAL, "BVH is not a tree");
+            if (d >= B200R_BVH_STACK_SIZE) return fail(ctx, B200R_EDEPTH, "BVH deeper than BVH_STACK_SIZE (32)");
+            if (nodes[i].a & 0x80000000u) {
+                if ((uint64_t)nodes[i].b + (nodes[i].a & 0x7fffffffu) > n_tri_idx)
+                    return fail(ctx, B200R_EINVAL, "BVH leaf range outside the triangle index list");
+            } else { st.push_back({nodes[i].b, d + 1}); st.push_back({nodes[i].a, d + 1}); }
+        }
+        for (uint32_t i = 0; i < n_tri_idx; i++)
+            if (tri_idx[i] < 0 || (uint32_t)tri_idx[i] >= n_tris) return fail(ctx, B200R_EINVAL, "tri_idx entry out of range");
+    }
+
+    std::vector<float4> hn, hl, hs, hv, ht;
+    if (nodes && n_nodes) {
+        hn.resize(2 * (size_t)n_nodes);
+        for (uint32_t i = 0; i < n_nodes; i++) {
+            hn[2 * i] = make_float4(nodes[i].lo[0], nodes[i].lo[1], nodes[i].lo[2], u2f(nodes[i].a));
+            hn[2 * i + 1] = make_float4(nodes[i].hi[0], nodes[i].hi[1], nodes[i].hi[2], u2f(nodes[i].b));
+        }
+        hl.resize(5 * (size_t)n_tri_idx);
+        for (uint32_t i = 0; i < n_tri_idx; i++) {
+            const uint32_t ti = (uint32_t)tri_idx[i];
+            const b200r_tri& t = tris[ti];
+            hl[5 * i + 0] = make_float4(t.normal[0], t.normal[1], t.normal[2], t.d);
+            hl[5 * i + 1] = make_float4(t.e1[0], t.e1[1], t.e1[2], t.d1);
+            hl[5 * i + 2] = make_float4(t.e2[0], t.e2[1], t.e2[2], t.d2);
+            hl[5 * i + 3] = make_float4(t.e3[0], t.e3[1], t.e3[2], t.d3);
+            hl[5 * i + 4] = make_float4(t.center[0], t.center[1], t.center[2], u2f((t.two_sided ? 0x80000000u : 0u) | ti));
+        }
+    }
+    hs.resize(6 * (size_t)n_tris); ht.resize(4 * (size_t)n_tris);
+    for (uint32_t i = 0; i < n_tris; i++) {
+        const b200r_tri& t = tris[i];
+        const b200r_vertex &A = verts[t.a], &B = verts[t.b], &C = verts[t.c];
+        float s[24] = {A.pos[0], A.pos[1], A.pos[2], B.pos[0], B.pos[1], B.pos[2], C.pos[0], C.pos[1], C.pos[2],
+                       A.nrm[0], A.nrm[1], A.nrm[2], B.nrm[0], B.nrm[1], B.nrm[2], C.nrm[0], C.nrm[1], C.nrm[2],
+                       u2f(A.ao), u2f(B.ao), u2f(C.ao), t.colorf[0], t.colorf[1], t.colorf[2]};
+        memcpy(&hs[6 * (size_t)i], s, sizeof s);
+        ht[4 * (size_t)i + 0] = make_float4(u2f(t.a), u2f(t.b), u2f(t.c), u2f(t.two_sided));
+        ht[4 * (size_t)i + 1] = make_float4(t.center[0], t.center[1], t.center[2], u2f(t.color));
+        ht[4 * (size_t)i + 2] = make_float4(t.normal[0], t.normal[1], t.normal[2], 0.f);
+        ht[4 * (size_t)i + 3] = make_float4(t.colorf[0], t.colorf[1], t.colorf[2], 0.f);
+    }
+    hv.resize(2 * (size_t)n_verts);
+    for (uint32_t i = 0; i < n_verts; i++) {
+        hv[2 * (size_t)i] = make_float4(verts[i].pos[0], verts[i].pos[1], verts[i].pos[2], u2f(verts[i].ao));
+        hv[2 * (size_t)i + 1] = make_float4(verts[i].nrm[0], verts[i].nrm[1], verts[i].nrm[2], 0.f);
+    }
+    CU(upload(&ctx->d_nodes, hn, ctx->stream));
+    CU(upload(&ctx->d_leaftris, hl, ctx->stream));
+    CU(upload(&ctx->d_shade, hs, ctx->stream));
+    CU(upload(&ctx->d_rverts, hv, ctx->stream));
+    CU(upload(&ctx->d_rtris, ht, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));   // host staging vectors go out of scope
+    ctx->sc.nodes = ctx->d_nodes; ctx->sc.leaftris = ctx->d_leaftris; ctx->sc.shade = ctx->d_shade;
+    ctx->sc.rverts = ctx->d_rverts; ctx->sc.rtris = ctx->d_rtris;
+    ctx->sc.n_nodes = n_nodes; ctx->sc.n_list = n_tri_idx; ctx->sc.n_tris = n_tris; ctx->sc.n_verts = n_verts;
+    ctx->have_scene = true; ctx->have_bvh = (nodes && n_nodes);
+    return B200R_OK;
+}
+
+int b200r_upload_shadowmap(b200r_ctx* ctx, int light, const float* map)
+{
+    if (!ctx || !map || light < 0 || light >= B200R_MAX_LIGHTS) return fail(ctx, B200R_EINVAL, "bad shadow map argument");
+    CU(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)B200R_SHADOWMAP_SIZE * B200R_SHADOWMAP_SIZE * 4;
+    if (!ctx->d_shadowmap[light]) CU(cudaMalloc((void**)&ctx->d_shadowmap[light], bytes));
+    CU(cudaMemcpyAsync(ctx->d_shadowmap[light], map, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->sc.shadowmap[light] = ctx->d_shadowmap[light];
+    return B200R_OK;
+}
+
+int b200r_render_shadowmap(b200r_ctx* ctx, int, const float*, const float*)
+{ return fail(ctx, B200R_EINVAL, "b200r_render_shadowmap: not implemented yet"); }
+
+int b200r_download_shadowmap(b200r_ctx* ctx, int light, float* map)
+{
+    if (!ctx || !map || light < 0 || light >= B200R_MAX_LIGHTS || !ctx->d_shadowmap[light])
+        return fail(ctx, B200R_EINVAL, "no such shadow map");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpy(map, ctx->d_shadowmap[light], (size_t)B200R_SHADOWMAP_SIZE * B200R_SHADOWMAP_SIZE * 4, cudaMemcpyDeviceToHost));
+    return B200R_OK;
+}
+
+int b200r_render_device(b200r_ctx* ctx, const b200r_frame* f, void* dev_xrgb, void* cuda_stream)
+{
+    if (!ctx) return fail(nullptr, B200R_EINVAL, "NULL ctx");
+    if (!dev_xrgb) return fail(ctx, B200R_EINVAL, "NULL device frame pointer");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    FrameParams fp;
+    int rc = render_common(ctx, f, (uint32_t*)dev_xrgb, s, fp);
+    if (rc) return rc;
+    if (!cuda_stream) {
+        CU(cudaStreamSynchronize(s));
+        CU(cudaEventElapsedTime(&ctx->last_total_ms, ctx->ev0, ctx->ev1));
+        ctx->last_dominant_ms = ctx->last_total_ms;
+    }
+    return B200R_OK;
+}
+
+int b200r_render(b200r_ctx* ctx, const b200r_frame* f, uint32_t* host_xrgb)
+{
+    if (!ctx) return fail(nullptr, B200R_EINVAL, "NULL ctx");
+    if (!host_xrgb) return fail(ctx, B200R_EINVAL, "NULL host frame pointer");
+    CU(cudaSetDevice(ctx->device));
+    FrameParams fp;
+    int rc = make_frame_params(ctx, f, fp);
+    if (rc) return rc;
+    const size_t words = (size_t)fp.W * fp.n_rows;
+    rc = ensure_frame(ctx, words);
+    if (rc) return rc;
+    if (ctx->pinned_words < words) {
+        if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+        ctx->h_pinned = nullptr; ctx->pinned_words = 0;
+        CU(cudaMallocHost((void**)&ctx->h_pinned, words * 4));
+        ctx->pinned_words = words;
+    }
+    rc = render_common(ctx, f, ctx->d_frame, ctx->stream, fp);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->h_pinned, ctx->d_frame, words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaEventElapsedTime(&ctx->last_total_ms, ctx->ev0, ctx->ev1));
+    ctx->last_dominant_ms = ctx->last_total_ms;
+    memcpy(host_xrgb, ctx->h_pinned, words * 4);
+    return B200R_OK;
+}
+
+int b200r_mlaa_device(b200r_ctx* ctx, void*, uint32_t, uint32_t, void*)
+{ return fail(ctx, B200R_EINVAL, "b200r_mlaa_device: not implemented yet"); }
+
+int b200r_deinterleave_device(b200r_ctx* ctx, const void*, void*, uint32_t, uint32_t, uint32_t, void*)
+{ return fail(ctx, B200R_EINVAL, "b200r_deinterleave_device: not implemented yet"); }
+
+int b200r_set_counters(b200r_ctx* ctx, int enabled)
+{
+    if (!ctx) return fail(nullptr, B200R_EINVAL, "NULL ctx");
+    ctx->counting = enabled != 0;
+    return B200R_OK;
+}
+
+int b200r_get_counters(b200r_ctx* ctx, b200r_counters* out)
+{
+    if (!ctx || !out) return fail(ctx, B200R_EINVAL, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    DeviceCounters h;
+    CU(cudaMemcpy(&h, ctx->d_ctr, sizeof h, cudaMemcpyDeviceToHost));
+    uint64_t* o = (uint64_t*)out;
+    for (int i = 0; i < 11; i++) o[i] = h.v[i];
+    return B200R_OK;
+}
+
+int b200r_last_kernel_ms(b200r_ctx* ctx, float* total_ms, float* dominant_ms)
+{
+    if (!ctx) return fail(nullptr, B200R_EINVAL, "NULL ctx");
+    if (total_ms) *total_ms = ctx->last_total_ms;
+    if (dominant_ms) *dominant_ms = ctx->last_dominant_ms;
+    return B200R_OK;
+}
+
+int b200r_last_launches(b200r_ctx* ctx, uint32_t* n)
+{
+    if (!ctx || !n) return fail(ctx, B200R_EINVAL, "NULL argument");
+    *n = ctx->last_launches;
+    return B200R_OK;
+}
+
+}  // extern "C"

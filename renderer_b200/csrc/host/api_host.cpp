@@ -64,3 +64,12 @@ const int32_t* b200r_scene_tri_idx(const b200r_scene* s, uint32_t* n)
 int b200r_scene_bvh_depth(const b200r_scene* s) { return s->s.bvh_depth; }
 
 }  // extern "C"
+
+extern "C" int b200r_upload_scene_handle(b200r_ctx* ctx, const b200r_scene* s)
+{
+    if (!s) { b200r::set_global_error("b200r_upload_scene_handle: NULL scene"); return B200R_EINVAL; }
+    const b200r::Scene& sc = s->s;
+    return b200r_upload_scene(ctx, sc.verts.data(), (uint32_t)sc.verts.size(), sc.tris.data(), (uint32_t)sc.tris.size(),
+                              sc.nodes.empty() ? nullptr : sc.nodes.data(), (uint32_t)sc.nodes.size(),
+                              sc.tri_idx.empty() ? nullptr : sc.tri_idx.data(), (uint32_t)sc.tri_idx.size());
+}

@@ -1,0 +1,75 @@
+"""GPU parity: the CUDA ray tracer (through the C-ABI) against the CPU restatement on the same inputs.
+
+Mirrors how one would test the reference: load a model, follow the `-b` orbit, render mode 9 / 0."""
+import pytest
+
+from util import assert_parity
+
+pytestmark = pytest.mark.gpu
+
+W, H = 320, 240
+
+
+@pytest.mark.parametrize("model,frames", [("torus.ply", [0, 37]), ("chessboard.tri", [0, 99]),
+                                          ("dragon_vis.ply", [1]), ("trainColor.tri", [5]), ("single.ply", [0])])
+def test_raytrace_default(rb, pyport, load_scene, gpu, model, frames):
+    s = load_scene(model)
+    gpu.upload(s)
+    for k, cam in rb.Orbit.cameras(frames).items():
+        f = rb.make_frame(rb.MODE_RAYTRACE, W, H, cam, frame_index=k)
+        assert_parity(gpu.render(f), pyport.render(s, f), f"{model} frame {k} mode 9")
+
+
+@pytest.mark.parametrize("flags", [0, 1, 2, 4, 3, 5, 6])   # all subsets of shadows/reflections/phong but the default
+def test_raytrace_feature_switches(rb, pyport, load_scene, gpu, flags):
+    s = load_scene("chessboard.tri")
+    gpu.upload(s)
+    cam = rb.Orbit.cameras([12])[12]
+    f = rb.make_frame(rb.MODE_RAYTRACE, W, H, cam, flags=flags)
+    assert_parity(gpu.render(f), pyport.render(s, f), f"chessboard flags={flags}")
+
+
+def test_raytrace_antialias_two_lights(rb, pyport, load_scene, gpu):
+    s = load_scene("torus.ply")
+    gpu.upload(s)
+    cam = rb.Orbit.cameras([3])[3]
+    f = rb.make_frame(rb.MODE_RAYTRACE_AA, W, H, cam, n_lights=2)
+    assert_parity(gpu.render(f), pyport.render(s, f), "torus AA 2 lights")
+
+
+@pytest.mark.parametrize("model", ["torus.ply", "chessboard.tri"])
+def test_raytrace_ambient_occlusion(rb, pyport, load_scene, gpu, model):
+    s = load_scene(model)
+    gpu.upload(s)
+    cam = rb.Orbit.cameras([2])[2]
+    f = rb.make_frame(rb.MODE_RAYTRACE, 160, 120, cam, flags=rb.F_DEFAULT | rb.F_AO, ao_samples=16, frame_index=2)
+    assert_parity(gpu.render(f), pyport.render(s, f), f"{model} AO x16")
+
+
+def test_counters_match_oracle(rb, pyport, load_scene, gpu):
+    s = load_scene("chessboard.tri")
+    gpu.upload(s)
+    cam = rb.Orbit.cameras([0])[0]
+    f = rb.make_frame(rb.MODE_RAYTRACE, W, H, cam, flags=rb.F_SHADOWS | rb.F_PHONG_NORMAL)
+    gpu.set_counters(True)
+    try:
+        img = gpu.render(f)
+        got = gpu.counters()
+    finally:
+        gpu.set_counters(False)
+    want_img, want = pyport.render(s, f, counters=True)
+    assert_parity(img, want_img, "chessboard counters frame")
+    for k in ("rays_primary", "rays_shadow", "rays_reflection", "rays_ao", "node_tests", "leaf_visits", "tri_tests"):
+        assert got[k] == want[k], (k, got[k], want[k])
+
+
+def test_row_sharding_matches_full_frame(rb, load_scene, gpu):
+    import numpy as np
+    s = load_scene("torus.ply")
+    gpu.upload(s)
+    cam = rb.Orbit.cameras([7])[7]
+    full = gpu.render(rb.make_frame(rb.MODE_RAYTRACE, W, H, cam))
+    P = 4
+    for r in range(P):
+        part = gpu.render(rb.make_frame(rb.MODE_RAYTRACE, W, H, cam, row_first=r, row_step=P))
+        assert np.array_equal(part, full[r::P])
