@@ -1,0 +1,411 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the B200-native renderer hot path.
+
+Metric (BASELINE.json): Mrays/s (and fps) at 1920x1080, at 1/2/4/8 GPUs, next to the reference's own
+OpenMP CPU path timed on the same box.  Workload = BASELINE config C2: chessboard.tri, mode 9
+(ray tracing: primary rays + Phong + one hard shadow ray per light, reflections off), one light, the
+reference's `-b` benchmark orbit (frame k of the orbit is step k).  One "step" = one frame.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c2r|c3|c5]
+
+N > 1 (launched by torchrun, one rank per GPU): the frame is sharded row-cyclically, every rank renders
+H/N rows, ONE NCCL all-gather of the packed rows, then a de-interleave kernel (strong scaling).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: model, W, H, mode, flags (1 shadows, 2 reflections, 4 phong normal, 8 AO), ao samples, ref-variant kwargs
+    "c2": dict(model="chessboard.tri", W=1920, H=1080, mode=9, flags=1 | 4, ao=0, ref=dict(no_reflections=True),
+               desc="chessboard.tri 1920x1080 mode 9: primary rays + Phong + 1 shadow ray, reflections off, 1 light"),
+    "c2r": dict(model="chessboard.tri", W=1920, H=1080, mode=9, flags=1 | 2 | 4, ao=0, ref=dict(),
+                desc="chessboard.tri 1920x1080 mode 9 reference defaults (reflections on)"),
+    "c3": dict(model="dragon_vis.ply", W=1920, H=1080, mode=9, flags=1 | 2 | 4 | 8, ao=16, ref=dict(ao=16),
+               desc="dragon_vis.ply 1920x1080 mode 9 + 16-sample AO + reflections"),
+    "c5": dict(model="chessboard.tri", W=3840, H=2160, mode=9, flags=1 | 2 | 4 | 8, ao=16, ref=dict(ao=16),
+               desc="chessboard.tri 3840x2160 mode 9 + reflections + 16-sample AO"),
+}
+
+
+def algorithmic_bytes(c, W, rows):
+    """32 B per node popped (inner test or leaf visit), 68 B per triangle tested (4-B index +
+    64 B of plane/edge data) + 16 B (centre + twoSided) because culling is on for every ray, + 4 B per pixel."""
+    return 32 * (c["node_tests"] + c["leaf_visits"]) + (68 + 16) * c["tri_tests"] + 4 * W * rows
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+
+class RefRunner:
+    """The unmodified reference (oracle/_ref/bin/renderer_<cfg>_fast: its own flags -O3 -ffast-math -mrecip
+    -fopenmp + SSE paths) run as `renderer -b -n N -m <mode> <model>`; fps from its own printout
+    (src/renderer.cc:631-633).  The per-scanline OpenMP fork/join (src/Raytracer.cc:558) does not scale to
+    very many threads, so the thread count is calibrated once (all cores, half, 32, 16) and the best is used
+    and reported as `cores`."""
+
+    def __init__(self, wl):
+        from oracle import pyport
+        self.pp = pyport
+        self.wl = wl
+        self.model = pyport.model_path(wl["model"])
+        kw = dict(wl["ref"]); kw["fast"] = True
+        self.exe = pyport.ref_exe(wl["W"], wl["H"], **kw)
+        self.ok = os.path.exists(self.exe) and os.path.exists(self.model)
+        self.threads = os.cpu_count() or 1
+        self.fps0 = None
+
+    def run(self, n, threads=None):
+        env = dict(os.environ); env["OMP_NUM_THREADS"] = str(threads or self.threads)
+        t = time.time()
+        r = subprocess.run([self.exe, "-b", "-n", str(n), "-m", str(self.wl["mode"] % 10), os.path.basename(self.model)],
+                           cwd=os.path.dirname(self.model), env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                           text=True, errors="replace")
+        wall = time.time() - t
+        got = self.pp.ref_fps(r.stdout)
+        return (got[2] if got and got[1] > 0 else n / max(wall, 1e-3))
+
+    def calibrate(self):
+        self.run(1)                               # builds/loads the .bvh cache, warms the page cache
+        nproc = os.cpu_count() or 1
+        best = (0.0, nproc)
+        for th in sorted({nproc, max(1, nproc // 2), min(32, nproc), min(16, nproc)}, reverse=True):
+            fps = self.run(3, th)
+            if fps > best[0]:
+                best = (fps, th)
+        self.fps0, self.threads = best
+        return best
+
+    def sample(self, seconds):
+        n = int(min(400, max(3, (self.fps0 or 3.0) * seconds)))
+        return n, self.run(n)
+
+
+def cpu_reference(wl, target_seconds=15.0, rays_per_frame=None, runner=None):
+    """Time the reference's own CPU implementation of the path on this box's host cores -> cpu_baseline object.
+    kind "reference" = the unmodified reference binary; falls back to the C++ restatement (kind "port") only
+    if that binary was not built."""
+    from oracle import pyport
+    if rays_per_frame is None:
+        rays_per_frame = port_rays_per_frame(wl)
+    r = runner or RefRunner(wl)
+    if r.ok:
+        if r.fps0 is None:
+            r.calibrate()
+        n, fps = r.sample(target_seconds)
+        return {"value": rays_per_frame * fps / 1e6, "unit": "Mrays/s", "fps": fps, "cores": r.threads,
+                "host_cpus": os.cpu_count(), "kind": "reference",
+                "sample": f"{n} orbit frames of [{wl['desc']}] by the unmodified reference built with its own flags "
+                          f"(-O3 -ffast-math -mrecip -fopenmp, SSE paths); OMP_NUM_THREADS={r.threads} (best of "
+                          f"all/half/32/16 on {os.cpu_count()} host CPUs); fps from its own printout"}
+    import renderer_b200 as rb
+    W, H = wl["W"], wl["H"]
+    model = pyport.model_path(wl["model"])
+    scene = rb.Scene(model).UpdateBoundingVolumeHierarchy(model + ".bvh")
+    cams = rb.Orbit.cameras(range(64))
+    t0 = time.time(); n = 0
+    while time.time() - t0 < target_seconds and n < 64:
+        f = rb.make_frame(wl["mode"], W, H, cams[n], flags=wl["flags"], ao_samples=wl["ao"] or 32, frame_index=n)
+        pyport.render(scene, f); n += 1
+    fps = n / (time.time() - t0)
+    return {"value": rays_per_frame * fps / 1e6, "unit": "Mrays/s", "fps": fps, "cores": os.cpu_count(),
+            "host_cpus": os.cpu_count(), "kind": "port",
+            "sample": f"{n} orbit frames of [{wl['desc']}] by oracle/port (C++ restatement, OpenMP over rows)"}
+
+
+def port_rays_per_frame(wl, frame=0):
+    """Rays (BVH_IntersectTriangles invocations) of one orbit frame, counted by the CPU restatement."""
+    import renderer_b200 as rb
+    from oracle import pyport
+    model = pyport.model_path(wl["model"])
+    scene = rb.Scene(model).UpdateBoundingVolumeHierarchy(model + ".bvh")
+    cam = rb.Orbit.cameras([frame])[frame]
+    f = rb.make_frame(wl["mode"], wl["W"], wl["H"], cam, flags=wl["flags"], ao_samples=wl["ao"] or 32, frame_index=frame)
+    _, c = pyport.render(scene, f, counters=True)
+    return c["rays_primary"] + c["rays_shadow"] + c["rays_reflection"] + c["rays_ao"]
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.time()
+    rays = port_rays_per_frame(wl)
+    # each "step" is a bounded sample: the reference renders a batch of orbit frames; K+W batches in total
+    per_step = max(1.5, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    runner = RefRunner(wl)
+    for i in range(args.warmup + args.steps):
+        cb = cpu_reference(wl, target_seconds=per_step, rays_per_frame=rays, runner=runner)
+        if i >= args.warmup:
+            vals.append(cb)
+    fps = sum(v["fps"] for v in vals) / len(vals)
+    val = rays * fps / 1e6
+    cb = dict(vals[-1]); cb["value"] = val; cb["fps"] = fps
+    line = {"impl": "reference", "metric": "Mrays/s", "value": val, "unit": "Mrays/s", "fps": fps, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / fps if fps else None,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "rays_per_frame": rays, "note": "reference CPU arm: no GPU involved"},
+            "cpu_baseline": cb,
+            "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.time() - t0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- B200 arm
+
+def run_b200_arm(args, wl):
+    import ctypes as C
+    import numpy as np
+    import torch
+    import renderer_b200 as rb
+    from oracle import pyport   # only for model staging paths and the cpu_baseline leg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    P = world
+    torch.cuda.set_device(local)
+    dist = None
+    if P > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    W, H = wl["W"], wl["H"]
+    model = pyport.model_path(wl["model"])
+    scene = rb.Scene(model).UpdateBoundingVolumeHierarchy(model + ".bvh")
+    gpu = rb.Renderer(local)
+    gpu.upload(scene)
+
+    K, Wm = args.steps, args.warmup
+    cams = rb.Orbit.cameras(range(K + Wm))
+    rows_per = (H + P - 1) // P
+
+    def frame_for(step, full=False):
+        return rb.make_frame(wl["mode"], W, H, cams[step], flags=wl["flags"], ao_samples=wl["ao"] or 32,
+                             frame_index=step, row_first=0 if full else rank, row_step=1 if full else P)
+
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+    shard = torch.zeros((rows_per, W), dtype=torch.int32, device="cuda")
+    gathered = torch.zeros((P * rows_per, W), dtype=torch.int32, device="cuda") if P > 1 else None
+    full = torch.zeros((H, W), dtype=torch.int32, device="cuda")
+    host = torch.zeros((H, W), dtype=torch.int32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+
+    def step_device(step):
+        """One frame, inputs resident, on torch's current stream. Returns my kernel launches."""
+        if P == 1:
+            gpu.render_device(frame_for(step), full.data_ptr(), sptr)
+            return 1
+        gpu.render_device(frame_for(step), shard.data_ptr(), sptr)
+        dist.all_gather_into_tensor(gathered, shard)
+        gpu.deinterleave_device(gathered.data_ptr(), full.data_ptr(), W, H, P, sptr)
+        return 2
+
+    def step_e2e(step):
+        """The user-facing call with HOST buffers: per-frame state in (kernel args), frame out to host memory."""
+        if P == 1:
+            gpu.render(frame_for(step), out=host_np)
+        else:
+            step_device(step)
+            if rank == 0:
+                host.copy_(full, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    host_np = host.numpy().view(np.uint32)
+
+    def barrier():
+        if P > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- counters of every timed frame (untimed counting pass; counting slows the kernel)
+    gpu.set_counters(True)
+    per_frame = []
+    for s in range(Wm, Wm + K):
+        gpu.render_device(frame_for(s, full=(P == 1)), (full if P == 1 else shard).data_ptr(), None)
+        per_frame.append(gpu.counters())
+    gpu.set_counters(False)
+    keys = ("rays_primary", "rays_shadow", "rays_reflection", "rays_ao", "node_tests", "leaf_visits", "tri_tests")
+    tot = {k: sum(c[k] for c in per_frame) for k in keys}
+    if P > 1:
+        t = torch.tensor([tot[k] for k in keys], dtype=torch.int64, device="cuda")
+        mine = t.clone()
+        dist.all_reduce(t)
+        tot_all = {k: int(v) for k, v in zip(keys, t.tolist())}
+        tot_mine = {k: int(v) for k, v in zip(keys, mine.tolist())}
+    else:
+        tot_all = tot_mine = tot
+    rays_total = tot_all["rays_primary"] + tot_all["rays_shadow"] + tot_all["rays_reflection"] + tot_all["rays_ao"]
+
+    # ---- device-timed run: W warm-up steps, then exactly K steps
+    for s in range(Wm):
+        step_device(s)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(K)]
+    launches = 0
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        flush.zero_()                       # evict the 126 MB L2 between timed iterations (not timed)
+        ev[i][0].record()
+        if P == 1:
+            launches += step_device(Wm + i)
+            ev[i][1].record()
+        else:
+            gpu.render_device(frame_for(Wm + i), shard.data_ptr(), sptr)
+            ev[i][1].record()
+            dist.all_gather_into_tensor(gathered, shard)
+            gpu.deinterleave_device(gathered.data_ptr(), full.data_ptr(), W, H, P, sptr)
+            launches += 2
+        ev[i][2].record()
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if sampler else None
+    step_ms = [e[0].elapsed_time(e[2]) for e in ev]
+    kern_ms = [e[0].elapsed_time(e[1]) for e in ev]
+    total_ms = sum(step_ms)
+    kern_total_ms = sum(kern_ms)
+    if P > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / K
+    fps = 1000.0 / ms_per_step
+    value = rays_total / (total_ms / 1000.0) / 1e6
+
+    # ---- end-to-end through the public call with host buffers
+    for s in range(min(Wm, 3)):
+        step_e2e(s)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        step_e2e(Wm + i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if P > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = rays_total / e2e_s / 1e6
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        # roofline of the dominant kernel (the ray-tracing kernel of THIS rank): algorithmic bytes / its duration
+        alg_bytes = algorithmic_bytes(tot_mine, W, (rows_per if P > 1 else H) * K)
+        achieved = alg_bytes / (kern_total_ms / 1000.0) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.workload)
+            except Exception:
+                traffic = None
+        cpu = None
+        if P == 1 and not args.no_cpu_baseline:
+            cpu = cpu_reference(wl, target_seconds=15.0, rays_per_frame=rays_total / K)
+        line = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "fps": fps, "n_gpus": P, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "camera": "reference -b orbit, one new frame per step",
+                       "rays_per_frame": rays_total / K, "l2": "flushed between timed steps (256 MiB write, outside the events)",
+                       "parallelism": "1 GPU" if P == 1 else f"row-cyclic sharding over {P} GPUs + 1 NCCL all-gather + de-interleave",
+                       "timing": "CUDA events on the launching stream, max over ranks"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "rt_frame_kernel", "kernel_ms": kern_total_ms / K,
+                         "algorithmic_bytes_per_launch": alg_bytes / K, "peak_source": peak_src + " (of measured)"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "fps": K / e2e_s,
+                    "h2d_bytes_per_step": C.sizeof(rb.Frame), "d2h_bytes_per_step": W * H * 4,
+                    "note": "b200r_render with a host frame buffer: frame state in, XRGB frame out, per step"},
+            "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall,
+        }
+        print(json.dumps(line))
+    if P > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    gpu.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+    else:
+        run_b200_arm(args, wl)
+
+
+if __name__ == "__main__":
+    main()

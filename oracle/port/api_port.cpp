@@ -27,6 +27,12 @@ int32_t oracle_ao_draw(uint32_t key, uint32_t n)
     return (int32_t)(v >> 1);
 }
 
+int oracle_supports(int mode, int mlaa)
+{
+    if (mlaa) return 0;
+    return mode == B200R_MODE_RAYTRACE || mode == B200R_MODE_RAYTRACE_AA;
+}
+
 int oracle_render(const oracle_scene* s, const b200r_frame* f, uint32_t* out, b200r_counters* ctr, int threads)
 {
     if (!s || !f || !out) return -1;

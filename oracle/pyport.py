@@ -90,6 +90,26 @@ def render(scene, frame, shadowmaps=(), threads=0, counters=False):
     return (out, ctr.as_dict()) if counters else out
 
 
+def supports(mode, mlaa=False):
+    """Which modes the restatement implements (grows as port/*.cpp grows)."""
+    L = port()
+    L.oracle_supports.restype = C.c_int
+    L.oracle_supports.argtypes = [C.c_int, C.c_int]
+    return bool(L.oracle_supports(int(mode), 1 if mlaa else 0))
+
+
+def shadowmaps_for(scene, frame):
+    """Shadow maps of the frame's lights, rendered by the restatement of Light::RenderSceneIntoShadowBuffer."""
+    import renderer_b200 as rb
+    maps = []
+    for i in range(frame.n_lights):
+        lp = tuple(frame.lights[i].pos)
+        w2l = (C.c_float * 9)()
+        rb.lib().b200r_light_world_to_light((C.c_float * 3)(*lp), w2l)
+        maps.append(render_shadowmap(scene, lp, tuple(w2l)))
+    return tuple(maps)
+
+
 def render_shadowmap(scene, light_pos, world2light):
     s = oscene(scene)
     m = np.empty((1024, 1024), dtype=np.float32)

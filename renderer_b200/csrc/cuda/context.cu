@@ -332,8 +332,17 @@ int b200r_render(b200r_ctx* ctx, const b200r_frame* f, uint32_t* host_xrgb)
 int b200r_mlaa_device(b200r_ctx* ctx, void*, uint32_t, uint32_t, void*)
 { return fail(ctx, B200R_EINVAL, "b200r_mlaa_device: not implemented yet"); }
 
-int b200r_deinterleave_device(b200r_ctx* ctx, const void*, void*, uint32_t, uint32_t, uint32_t, void*)
-{ return fail(ctx, B200R_EINVAL, "b200r_deinterleave_device: not implemented yet"); }
+int b200r_deinterleave_device(b200r_ctx* ctx, const void* dev_gathered, void* dev_frame, uint32_t width,
+                              uint32_t height, uint32_t n_shards, void* cuda_stream)
+{
+    if (!ctx || !dev_gathered || !dev_frame || !width || !height || !n_shards)
+        return fail(ctx, B200R_EINVAL, "b200r_deinterleave_device: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    CU(launch_deinterleave((const uint32_t*)dev_gathered, (uint32_t*)dev_frame, width, height, n_shards, ctx->numSMs, s));
+    if (!cuda_stream) CU(cudaStreamSynchronize(s));
+    return B200R_OK;
+}
 
 int b200r_set_counters(b200r_ctx* ctx, int enabled)
 {

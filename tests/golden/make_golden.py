@@ -1,0 +1,83 @@
+#!/usr/bin/env python3
+"""Generate the golden frames under tests/golden/ from the UNMODIFIED reference (oracle/_ref builds).
+
+Run where /root/reference is mounted:   python tests/golden/make_golden.py
+Every case is one run of `renderer_<variant> -b -n N -m <mode> [-w] <model>` (the reference's own
+benchmark orbit); the presented frames are stored losslessly (npz, zlib) with their SHA-256.
+The reference itself ships no golden vectors or tests, so these are the pin.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import pyport  # noqa: E402
+
+W, H = 320, 240
+
+# name: (model, mode, frames, two_lights, variant kwargs, env)
+CASES = {
+    # ray tracer (reference defaults: shadows + reflections + phong normal)
+    "rt_torus_m9": ("torus.ply", 9, [0, 37], False, {}, {}),
+    "rt_chess_m9": ("chessboard.tri", 9, [0, 99], False, {}, {}),
+    "rt_dragon_m9": ("dragon_vis.ply", 9, [1], False, {}, {}),
+    "rt_train_m9_w": ("trainColor.tri", 9, [5], True, {}, {}),
+    "rt_torus_m0": ("torus.ply", 0, [3], False, {}, {}),
+    "rt_chess_m9_norefl": ("chessboard.tri", 9, [0, 12], False, {"no_reflections": True}, {}),
+    "rt_torus_m9_ao16": ("torus.ply", 9, [2], False, {"ao": 16}, {"OMP_NUM_THREADS": "4"}),
+    "rt_chess_m9_ao16": ("chessboard.tri", 9, [2], False, {"ao": 16}, {"OMP_NUM_THREADS": "4"}),
+    # rasteriser: strict build, single-threaded so the (benign) Z-buffer races of the reference cannot occur
+    "ras_torus_m1": ("torus.ply", 1, [0, 37], False, {}, {"OMP_NUM_THREADS": "1"}),
+    "ras_torus_m2": ("torus.ply", 2, [0, 37], False, {}, {"OMP_NUM_THREADS": "1"}),
+    "ras_torus_m3": ("torus.ply", 3, [0, 37], False, {}, {"OMP_NUM_THREADS": "1"}),
+    "ras_statue_m4": ("statue.ply", 4, [0, 50], False, {}, {"OMP_NUM_THREADS": "1"}),
+    "ras_statue_m5": ("statue.ply", 5, [0, 50], False, {}, {"OMP_NUM_THREADS": "1"}),
+    "ras_statue_m6": ("statue.ply", 6, [0, 50], False, {}, {"OMP_NUM_THREADS": "1"}),
+    "ras_statue_m7": ("statue.ply", 7, [0, 50], False, {}, {"OMP_NUM_THREADS": "1"}),
+    "ras_statue_m8": ("statue.ply", 8, [0, 50], False, {}, {"OMP_NUM_THREADS": "1"}),
+    "ras_chess_m6": ("chessboard.tri", 6, [0], False, {}, {"OMP_NUM_THREADS": "1"}),
+    "ras_chess_m8_w": ("chessboard.tri", 8, [10], True, {}, {"OMP_NUM_THREADS": "1"}),
+    "ras_train_m8": ("trainColor.tri", 8, [0, 20], False, {}, {"OMP_NUM_THREADS": "1"}),
+    "ras_chess_m3": ("chessboard.tri", 3, [0], False, {}, {"OMP_NUM_THREADS": "1"}),
+    "ras_dragon_m2": ("dragon_vis.ply", 2, [4], False, {}, {"OMP_NUM_THREADS": "1"}),
+    # MLAA post filter (built --enable-mlaa equivalent)
+    "mlaa_statue_m6": ("statue.ply", 6, [0], False, {"mlaa": True}, {"OMP_NUM_THREADS": "1"}),
+    "mlaa_chess_m9": ("chessboard.tri", 9, [0], False, {"mlaa": True}, {}),
+    "mlaa_train_m8": ("trainColor.tri", 8, [7], False, {"mlaa": True}, {"OMP_NUM_THREADS": "1"}),
+}
+
+
+def main():
+    only = set(sys.argv[1:])
+    index_path = os.path.join(HERE, "index.json")
+    index = json.load(open(index_path)) if os.path.exists(index_path) else {}
+    for name, (model, mode, frames, two, kw, env) in CASES.items():
+        if only and name not in only:
+            continue
+        if not pyport.have_ref(W, H, **kw):
+            pyport.build_ref(W, H, **kw)
+        imgs, _ = pyport.run_ref(pyport.model_path(model), mode, W, H, frames, two_lights=two, env=env, **kw)
+        arrs = {f"frame_{k}": v for k, v in imgs.items()}
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrs)
+        index[name] = {"model": model, "mode": mode, "frames": frames, "two_lights": two, "variant": kw,
+                       "width": W, "height": H,
+                       "sha256": {str(k): hashlib.sha256(v.tobytes()).hexdigest() for k, v in imgs.items()}}
+        print(name, {k: int((v != 0).sum()) for k, v in imgs.items()})
+    # the reference's own .bvh caches (byte-level pin of loader + BVH builder)
+    bvh = {}
+    for m in sorted(os.listdir(pyport.MODELS)):
+        p = os.path.join(pyport.MODELS, m + "") if m.endswith(".bvh") else None
+        if p:
+            bvh[m[:-4]] = hashlib.sha256(open(p, "rb").read()).hexdigest()
+    if bvh:
+        index["_bvh_sha256"] = bvh
+    json.dump(index, open(index_path, "w"), indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

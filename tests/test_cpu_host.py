@@ -1,0 +1,73 @@
+"""CPU: host plumbing (loader, BVH, cache, orbit, lights) against what the reference produced."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+INDEX = json.load(open(os.path.join(HERE, "golden", "index.json")))
+
+
+@pytest.mark.parametrize("model", sorted(INDEX["_bvh_sha256"]))
+def test_bvh_is_byte_identical_to_reference_cache(rb, pyport, model):
+    """Scene::load + CreateBVH + CreateCFBVH: our .bvh bytes == the .bvh the reference wrote for the model."""
+    path = pyport.model_path(model)
+    if not os.path.exists(path):
+        pytest.skip("model not staged")
+    s = rb.Scene(path).UpdateBoundingVolumeHierarchy(None, forceRecalc=True)
+    assert hashlib.sha256(s.bvh_bytes()).hexdigest() == INDEX["_bvh_sha256"][model]
+    assert 0 <= s.bvh_depth < 32
+
+
+def test_bvh_cache_roundtrip_and_interop(rb, pyport, tmp_path):
+    path = pyport.model_path("torus.ply")
+    if not os.path.exists(path):
+        pytest.skip("model not staged")
+    cache = str(tmp_path / "torus.ply.bvh")
+    a = rb.Scene(path).UpdateBoundingVolumeHierarchy(cache)
+    assert hashlib.sha256(open(cache, "rb").read()).hexdigest() == INDEX["_bvh_sha256"]["torus.ply"]
+    b = rb.Scene(path).UpdateBoundingVolumeHierarchy(cache)          # now read from the cache
+    assert a.bvh_bytes() == b.bvh_bytes()
+    open(cache, "wb").write(b"\x01\x02\x03")                          # short/corrupt cache -> silent rebuild
+    c = rb.Scene(path).UpdateBoundingVolumeHierarchy(cache)
+    assert c.bvh_bytes() == a.bvh_bytes()
+
+
+def test_loader_errors_like_the_reference(rb, tmp_path):
+    with pytest.raises(rb.RendererError, match="not found|Missing"):
+        rb.Scene(str(tmp_path / "nope.tri"))
+    p = tmp_path / "x.obj"; p.write_text("hi")
+    with pytest.raises(rb.RendererError, match="extension"):
+        rb.Scene(str(p))
+    q = tmp_path / "bad.tri"; q.write_bytes(b"\xde\xc0\xad\xde" + b"\x05\x00\x00\x00" + b"\x00" * 7)
+    with pytest.raises(rb.RendererError, match="Malformed"):
+        rb.Scene(str(q))
+
+
+def test_tiny_ply_and_counts(rb, pyport):
+    path = pyport.model_path("single.ply")
+    if not os.path.exists(path):
+        pytest.skip("model not staged")
+    s = rb.Scene(path).UpdateBoundingVolumeHierarchy()
+    assert s.n_triangles == 1 and s.n_nodes == 1 and s.bvh_depth == 0
+    c = rb.Scene(pyport.model_path("chessboard.tri"))
+    assert (c.n_vertices, c.n_triangles) == (32488, 46658)
+
+
+def test_orbit_is_the_reference_recurrence(rb):
+    cams = rb.Orbit.cameras([0, 1, 99])
+    e0 = np.array(cams[0].eye[:])
+    assert abs(np.linalg.norm(e0) - 4.8) < 1e-5 and e0[2] == 0.0 and e0[1] < 0      # angle1 = -0.3 deg
+    e99 = np.array(cams[99].eye[:])
+    assert abs(np.degrees(np.arctan2(-e99[1], e99[0])) - 30.0) < 1e-3               # 100 steps of 0.3 deg
+    mv = np.array(cams[0].mv[:]).reshape(3, 3)
+    assert np.allclose(mv @ mv.T, np.eye(3), atol=1e-6)
+    assert np.allclose(mv[2], -e0 / np.linalg.norm(e0), atol=1e-6)                  # forward looks at the origin
+
+
+def test_default_lights(rb):
+    l0, l1 = rb.default_light_pos(0), rb.default_light_pos(1)
+    assert np.allclose(l0, (3.394113, 3.394113, 4.8), atol=1e-5)
+    assert np.allclose(l1, (4.8, -4.8, 4.8), atol=1e-6)
