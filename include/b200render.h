@@ -160,6 +160,11 @@ int  b200r_mlaa_device(b200r_ctx* ctx, void* dev_xrgb, uint32_t width, uint32_t 
 int  b200r_deinterleave_device(b200r_ctx* ctx, const void* dev_gathered, void* dev_frame,
                                uint32_t width, uint32_t height, uint32_t n_shards, void* cuda_stream);
 
+/* Numerics self-test: the slab test's shared-reciprocal divide (DESIGN.md "division") against the compiler's IEEE
+ * divide on `samples` random operand pairs drawn from the whole domain in which the fast path is used.
+ * *mismatches must come back 0. first_bad (optional) receives {a, d, a/d, fast} of the first mismatch. */
+int  b200r_selftest_division(b200r_ctx* ctx, uint64_t samples, uint32_t seed, uint64_t* mismatches, float first_bad[4]);
+
 int  b200r_set_counters(b200r_ctx* ctx, int enabled);   /* counting costs time; off by default */
 int  b200r_get_counters(b200r_ctx* ctx, b200r_counters* out);
 /* Device time (ms, CUDA events on the launching stream) of the kernels of the last frame. */

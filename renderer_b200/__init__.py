@@ -213,6 +213,13 @@ class Renderer:
         _check(lib().b200r_download_shadowmap(self._ctx, light, m.ctypes.data), self._ctx)
         return m
 
+    def selftest_division(self, samples=1 << 32, seed=1):
+        """(#mismatches, first_bad) of the shared-reciprocal divide vs the IEEE divide (must be 0)."""
+        m = C.c_uint64()
+        fb = (C.c_float * 4)()
+        _check(lib().b200r_selftest_division(self._ctx, samples, seed, C.byref(m), fb), self._ctx)
+        return m.value, tuple(fb)
+
     def set_counters(self, enabled):
         _check(lib().b200r_set_counters(self._ctx, 1 if enabled else 0), self._ctx)
 

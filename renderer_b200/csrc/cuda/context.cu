@@ -3,6 +3,7 @@
 // b200r_render() stands where main()'s switch(mode) calls scene.renderXxx(sony, canvas)
 // (reference src/renderer.cc:522-583). There is deliberately NO CPU rendering path in this library:
 // if CUDA is unavailable b200r_init() fails and nothing can be rendered.
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -213,12 +214,38 @@ int b200r_upload_scene(b200r_ctx* ctx, const b200r_vertex* verts, uint32_t n_ver
     }
 
     std::vector<float4> hn, hl, hs, hv, ht;
+    uint32_t root_ref = 0xFFFFFFFFu, fast_ok = 1;
+    float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
     if (nodes && n_nodes) {
-        hn.resize(2 * (size_t)n_nodes);
+        // inner nodes get consecutive record ids in DFS order; a child ref is a record id or a leaf ref
+        std::vector<uint32_t> inner_id(n_nodes, 0xFFFFFFFFu);
+        uint32_t n_inner = 0;
+        for (uint32_t i = 0; i < n_nodes; i++) if (!(nodes[i].a & 0x80000000u)) inner_id[i] = n_inner++;
+        if (n_inner >= 0x80000000u || n_tri_idx >= 0x3fffffffu) return fail(ctx, B200R_EINVAL, "scene too large");
+        auto ref_of = [&](uint32_t i) -> uint32_t {
+            if (!(nodes[i].a & 0x80000000u)) return inner_id[i];
+            return (nodes[i].a & 0x7fffffffu) ? (0x80000000u | nodes[i].b) : 0xFFFFFFFFu;
+        };
+        auto check = [&](float v) {
+            const float a = fabsf(v);
+            if (!(a == 0.f || (a >= 2.9103830456733704e-11f && a <= 1.125899906842624e15f))) fast_ok = 0;
+        };
+        hn.resize(4 * (size_t)n_inner);
         for (uint32_t i = 0; i < n_nodes; i++) {
-            hn[2 * i] = make_float4(nodes[i].lo[0], nodes[i].lo[1], nodes[i].lo[2], u2f(nodes[i].a));
-            hn[2 * i + 1] = make_float4(nodes[i].hi[0], nodes[i].hi[1], nodes[i].hi[2], u2f(nodes[i].b));
+            for (int c = 0; c < 3; c++) { check(nodes[i].lo[c]); check(nodes[i].hi[c]); }
+            if (nodes[i].a & 0x80000000u) continue;
+            const b200r_bvhnode &L = nodes[nodes[i].a], &R = nodes[nodes[i].b];
+            float4* rec = &hn[4 * (size_t)inner_id[i]];
+            rec[0] = make_float4(L.lo[0], L.hi[0], R.lo[0], R.hi[0]);
+            rec[1] = make_float4(L.lo[1], L.hi[1], R.lo[1], R.hi[1]);
+            rec[2] = make_float4(L.lo[2], L.hi[2], R.lo[2], R.hi[2]);
+            rec[3] = make_float4(u2f(ref_of(nodes[i].a)), u2f(ref_of(nodes[i].b)), 0.f, 0.f);
         }
+        root_ref = ref_of(0);
+        for (int c = 0; c < 3; c++) { root_lo[c] = nodes[0].lo[c]; root_hi[c] = nodes[0].hi[c]; }
+        std::vector<char> last(n_tri_idx, 0);
+        for (uint32_t i = 0; i < n_nodes; i++)
+            if ((nodes[i].a & 0x80000000u) && (nodes[i].a & 0x7fffffffu)) last[nodes[i].b + (nodes[i].a & 0x7fffffffu) - 1] = 1;
         hl.resize(5 * (size_t)n_tri_idx);
         for (uint32_t i = 0; i < n_tri_idx; i++) {
             const uint32_t ti = (uint32_t)tri_idx[i];
@@ -227,8 +254,10 @@ int b200r_upload_scene(b200r_ctx* ctx, const b200r_vertex* verts, uint32_t n_ver
             hl[5 * i + 1] = make_float4(t.e1[0], t.e1[1], t.e1[2], t.d1);
             hl[5 * i + 2] = make_float4(t.e2[0], t.e2[1], t.e2[2], t.d2);
             hl[5 * i + 3] = make_float4(t.e3[0], t.e3[1], t.e3[2], t.d3);
-            hl[5 * i + 4] = make_float4(t.center[0], t.center[1], t.center[2], u2f((t.two_sided ? 0x80000000u : 0u) | ti));
+            hl[5 * i + 4] = make_float4(t.center[0], t.center[1], t.center[2],
+                                        u2f((t.two_sided ? 0x80000000u : 0u) | (last[i] ? 0x40000000u : 0u) | ti));
         }
+        if (n_tris >= 0x3fffffffu) return fail(ctx, B200R_EINVAL, "scene too large");
     }
     hs.resize(6 * (size_t)n_tris); ht.resize(4 * (size_t)n_tris);
     for (uint32_t i = 0; i < n_tris; i++) {
@@ -254,9 +283,11 @@ int b200r_upload_scene(b200r_ctx* ctx, const b200r_vertex* verts, uint32_t n_ver
     CU(upload(&ctx->d_rverts, hv, ctx->stream));
     CU(upload(&ctx->d_rtris, ht, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));   // host staging vectors go out of scope
-    ctx->sc.nodes = ctx->d_nodes; ctx->sc.leaftris = ctx->d_leaftris; ctx->sc.shade = ctx->d_shade;
+    ctx->sc.wnodes = ctx->d_nodes; ctx->sc.leaftris = ctx->d_leaftris; ctx->sc.shade = ctx->d_shade;
     ctx->sc.rverts = ctx->d_rverts; ctx->sc.rtris = ctx->d_rtris;
     ctx->sc.n_nodes = n_nodes; ctx->sc.n_list = n_tri_idx; ctx->sc.n_tris = n_tris; ctx->sc.n_verts = n_verts;
+    ctx->sc.root_ref = root_ref; ctx->sc.fast_div_ok = fast_ok;
+    memcpy(ctx->sc.root_lo, root_lo, 12); memcpy(ctx->sc.root_hi, root_hi, 12);
     ctx->have_scene = true; ctx->have_bvh = (nodes && n_nodes);
     return B200R_OK;
 }
@@ -341,6 +372,24 @@ int b200r_deinterleave_device(b200r_ctx* ctx, const void* dev_gathered, void* de
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     CU(launch_deinterleave((const uint32_t*)dev_gathered, (uint32_t*)dev_frame, width, height, n_shards, ctx->numSMs, s));
     if (!cuda_stream) CU(cudaStreamSynchronize(s));
+    return B200R_OK;
+}
+
+int b200r_selftest_division(b200r_ctx* ctx, uint64_t samples, uint32_t seed, uint64_t* mismatches, float first_bad[4])
+{
+    if (!ctx || !mismatches) return fail(ctx, B200R_EINVAL, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    unsigned long long* d_m = nullptr; float* d_f = nullptr;
+    CU(cudaMalloc((void**)&d_m, 8)); CU(cudaMalloc((void**)&d_f, 16));
+    CU(cudaMemsetAsync(d_m, 0, 8, ctx->stream)); CU(cudaMemsetAsync(d_f, 0, 16, ctx->stream));
+    CU(launch_division_selftest(samples, seed, d_m, d_f, ctx->numSMs, ctx->stream));
+    unsigned long long m = 0; float fb[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(&m, d_m, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(fb, d_f, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_m); cudaFree(d_f);
+    *mismatches = m;
+    if (first_bad) memcpy(first_bad, fb, 16);
     return B200R_OK;
 }
 

@@ -1,10 +1,16 @@
 // device_types.cuh — device-side layout of the scene and per-frame parameters.
 //
 // HBM layout (uploaded once by b200r_upload_scene, see DESIGN.md "data layout"):
-//   nodes      2 x float4 per BVH node   {lo.xyz, bits(a)} {hi.xyz, bits(b)}        (= CacheFriendlyBVHNode, 32 B)
+//   wnodes     4 x float4 (64 B) per INNER BVH node: the boxes of its two children side by side, so one fetch
+//              feeds both child slab tests:  {L.lo.x, L.hi.x, R.lo.x, R.hi.x} {..y..} {..z..} {Lref, Rref, 0, 0}
+//              ref = index of the child's own record if the child is an inner node, else 0x80000000 | start of the
+//              child leaf in the list below (0xFFFFFFFF for an empty leaf). The reference tests a node's box when
+//              it is popped and never tests leaf boxes (src/Raytracer.cc:224-229); testing a child's box at push
+//              time instead visits exactly the same leaves. The root's own box lives in DeviceScene (root_lo/hi).
 //   leaftris   5 x float4 per entry of the triangle index list, IN LIST ORDER (the triIdx indirection of
 //              reference src/Raytracer.cc:240 is baked out; order inside each leaf is preserved):
-//                {n.xyz, d} {e1.xyz, d1} {e2.xyz, d2} {e3.xyz, d3} {center.xyz, bits(twoSided<<31 | triIndex)}
+//                {n.xyz, d} {e1.xyz, d1} {e2.xyz, d2} {e3.xyz, d3}
+//                {center.xyz, bits(twoSided<<31 | lastInLeaf<<30 | triIndex)}
 //   shade      6 x float4 per triangle (by triangle index): A, B, C positions, nA, nB, nC, ao[3], colorf[3]
 //   rverts     vertices as {pos.xyz, bits(ao)} {nrm.xyz, 0}  (rasteriser / points)
 //   rtris      per-triangle raster record (rasteriser setup)
@@ -18,13 +24,16 @@
 namespace b200r {
 
 struct DeviceScene {
-    const float4* nodes;      // 2 per node
+    const float4* wnodes;     // 4 per inner node
     const float4* leaftris;   // 5 per list entry
     const float4* shade;      // 6 per triangle
     const float4* rverts;     // 2 per vertex
     const float4* rtris;      // 4 per triangle: {a,b,c,two_sided} {center, color bits} {normal, 0} {colorf, 0}
     const float*  shadowmap[B200R_MAX_LIGHTS];
     uint32_t n_nodes, n_list, n_tris, n_verts;
+    uint32_t root_ref;        // ref of the root (inner record 0, or a leaf ref for tiny scenes)
+    uint32_t fast_div_ok;     // every node bound is 0 or in [2^-35, 2^50]: precondition of the shared-reciprocal divide
+    float root_lo[3], root_hi[3];
 };
 
 struct FrameParams {
