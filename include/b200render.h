@@ -165,6 +165,11 @@ int  b200r_deinterleave_device(b200r_ctx* ctx, const void* dev_gathered, void* d
  * *mismatches must come back 0. first_bad (optional) receives {a, d, a/d, fast} of the first mismatch. */
 int  b200r_selftest_division(b200r_ctx* ctx, uint64_t samples, uint32_t seed, uint64_t* mismatches, float first_bad[4]);
 
+/* Developer tool: per-tile (8x4 pixels) start/end device timestamps (ns, %globaltimer) of the last ray-traced frame;
+ * tile t = (row of tiles)*ceil(W/8) + column. Costs time; off by default. */
+int  b200r_set_tile_profile(b200r_ctx* ctx, int enabled);
+int  b200r_get_tile_profile(b200r_ctx* ctx, uint64_t* start_end_ns, uint32_t max_tiles, uint32_t* n_tiles);
+
 int  b200r_set_counters(b200r_ctx* ctx, int enabled);   /* counting costs time; off by default */
 int  b200r_get_counters(b200r_ctx* ctx, b200r_counters* out);
 /* Device time (ms, CUDA events on the launching stream) of the kernels of the last frame. */

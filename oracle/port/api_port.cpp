@@ -30,7 +30,8 @@ int32_t oracle_ao_draw(uint32_t key, uint32_t n)
 int oracle_supports(int mode, int mlaa)
 {
     if (mlaa) return 0;
-    return mode == B200R_MODE_RAYTRACE || mode == B200R_MODE_RAYTRACE_AA;
+    return mode == B200R_MODE_RAYTRACE || mode == B200R_MODE_RAYTRACE_AA || mode == B200R_MODE_POINTS ||
+           mode == B200R_MODE_POINTS_TRI || (mode >= B200R_MODE_AMBIENT && mode <= B200R_MODE_PHONG_SOFTSHADOWMAPS);
 }
 
 int oracle_render(const oracle_scene* s, const b200r_frame* f, uint32_t* out, b200r_counters* ctr, int threads)
@@ -44,6 +45,17 @@ int oracle_render(const oracle_scene* s, const b200r_frame* f, uint32_t* out, b2
         if (!s->nodes) return -1;
         oport::render_raytrace(s, f, out, ctr, threads);
         break;
+    case B200R_MODE_PHONG_SHADOWMAPS:
+    case B200R_MODE_PHONG_SOFTSHADOWMAPS:
+        for (uint32_t i = 0; i < f->n_lights; i++) if (!s->shadowmap[i]) return -4;
+        /* fallthrough */
+    case B200R_MODE_POINTS:
+    case B200R_MODE_POINTS_TRI:
+    case B200R_MODE_AMBIENT:
+    case B200R_MODE_GOURAUD:
+    case B200R_MODE_PHONG:
+        oport::render_raster(s, f, out, ctr, threads);
+        break;
     default:
         return -2;
     }
@@ -53,5 +65,4 @@ int oracle_render(const oracle_scene* s, const b200r_frame* f, uint32_t* out, b2
 }  // extern "C"
 
 // (raster / shadow-map / MLAA restatements live in raster_port.cpp / mlaa_port.cpp)
-extern "C" __attribute__((weak)) int oracle_render_shadowmap(const oracle_scene*, const float*, const float*, float*) { return -3; }
 extern "C" __attribute__((weak)) int oracle_mlaa(uint32_t*, int, int) { return -3; }

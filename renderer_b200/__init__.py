@@ -220,6 +220,19 @@ class Renderer:
         _check(lib().b200r_selftest_division(self._ctx, samples, seed, C.byref(m), fb), self._ctx)
         return m.value, tuple(fb)
 
+    def tile_profile(self, frame):
+        """Developer tool: render `frame` with per-tile timestamps -> (n_tiles, 2) uint64 array of start/end ns."""
+        _check(lib().b200r_set_tile_profile(self._ctx, 1), self._ctx)
+        try:
+            self.render(frame)
+            n = C.c_uint32()
+            _check(lib().b200r_get_tile_profile(self._ctx, None, 0, C.byref(n)), self._ctx)
+            out = np.zeros((n.value, 2), dtype=np.uint64)
+            _check(lib().b200r_get_tile_profile(self._ctx, out.ctypes.data, n.value, C.byref(n)), self._ctx)
+        finally:
+            _check(lib().b200r_set_tile_profile(self._ctx, 0), self._ctx)
+        return out
+
     def set_counters(self, enabled):
         _check(lib().b200r_set_counters(self._ctx, 1 if enabled else 0), self._ctx)
 

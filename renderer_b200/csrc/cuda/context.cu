@@ -37,6 +37,11 @@ struct b200r_ctx {
     uint32_t* h_pinned = nullptr; size_t pinned_words = 0;
     unsigned* d_tileCounter = nullptr;
     DeviceCounters* d_ctr = nullptr;
+    RasterBuffers rb{};
+    size_t zkey_pixels = 0;
+    unsigned* h_spanCount = nullptr;          // pinned
+    unsigned long long* d_tileProf = nullptr; size_t tileProfTiles = 0; bool tileProfile = false; uint32_t lastTiles = 0;
+    unsigned* d_shadowKeys = nullptr;
     bool counting = false;
     float last_total_ms = 0.f, last_dominant_ms = 0.f;
     uint32_t last_launches = 0;
@@ -123,9 +128,66 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
     case B200R_MODE_RAYTRACE:
     case B200R_MODE_RAYTRACE_AA:
         if (!ctx->have_bvh) return fail(ctx, B200R_ESTATE, "ray tracing needs a BVH (nodes/tri_idx were not uploaded)");
-        CU(launch_raytrace(ctx->sc, fp, d_out, ctx->d_tileCounter, ctx->d_ctr, ctx->counting, ctx->numSMs, stream));
+        {
+            const uint32_t nTiles = ((fp.W + 7) / 8) * ((fp.n_rows + 3) / 4);
+            unsigned long long* prof = nullptr;
+            if (ctx->tileProfile) {
+                if (ctx->tileProfTiles < nTiles) {
+                    if (ctx->d_tileProf) cudaFree(ctx->d_tileProf);
+                    ctx->d_tileProf = nullptr; ctx->tileProfTiles = 0;
+                    CU(cudaMalloc((void**)&ctx->d_tileProf, (size_t)nTiles * 16));
+                    ctx->tileProfTiles = nTiles;
+                }
+                prof = ctx->d_tileProf; ctx->lastTiles = nTiles;
+            }
+            CU(launch_raytrace(ctx->sc, fp, d_out, ctx->d_tileCounter, ctx->d_ctr, ctx->counting, prof, ctx->numSMs, stream));
+        }
         ctx->last_launches += 1;
         break;
+    case B200R_MODE_PHONG_SHADOWMAPS:
+    case B200R_MODE_PHONG_SOFTSHADOWMAPS:
+        for (uint32_t i = 0; i < fp.n_lights; i++)
+            if (!ctx->sc.shadowmap[i])
+                return fail(ctx, B200R_ESTATE, "modes 7/8 need a shadow map per light (b200r_render_shadowmap / b200r_upload_shadowmap)");
+        /* fallthrough */
+    case B200R_MODE_POINTS:
+    case B200R_MODE_POINTS_TRI:
+    case B200R_MODE_AMBIENT:
+    case B200R_MODE_GOURAUD:
+    case B200R_MODE_PHONG: {
+        const size_t px = (size_t)fp.W * fp.n_rows;
+        if (ctx->zkey_pixels < px) {
+            if (ctx->rb.zkeys) cudaFree(ctx->rb.zkeys);
+            ctx->rb.zkeys = nullptr; ctx->zkey_pixels = 0;
+            CU(cudaMalloc((void**)&ctx->rb.zkeys, px * 8));
+            ctx->zkey_pixels = px;
+        }
+        if (!ctx->rb.spans) {
+            ctx->rb.spanCapacity = 1u << 20;
+            CU(cudaMalloc((void**)&ctx->rb.spans, (size_t)ctx->rb.spanCapacity * 80));
+        }
+        for (int attempt = 0;; attempt++) {
+            int launches = 0;
+            CU(launch_raster(ctx->sc, fp, d_out, ctx->rb, ctx->d_ctr, ctx->counting, ctx->numSMs, stream, launches));
+            ctx->last_launches += (uint32_t)launches;
+            if (fp.mode <= B200R_MODE_POINTS_TRI) break;
+            // the span buffer is sized by doubling: a frame that overflowed is simply rendered again
+            CU(cudaMemcpyAsync(ctx->h_spanCount, ctx->rb.spanCount, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+            const unsigned need = *ctx->h_spanCount;
+            if (need <= ctx->rb.spanCapacity) break;
+            if (attempt >= 2) return fail(ctx, B200R_ENOMEM, "span buffer overflow persisted");
+            unsigned cap = ctx->rb.spanCapacity;
+            while (cap < need) cap *= 2;
+            cudaFree(ctx->rb.spans); ctx->rb.spans = nullptr;
+            CU(cudaMalloc((void**)&ctx->rb.spans, (size_t)cap * 80));
+            ctx->rb.spanCapacity = cap;
+            if (ctx->counting) CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(DeviceCounters), stream));
+            ctx->last_launches = 0;
+            CU(cudaEventRecord(ctx->ev0, stream));
+        }
+        break;
+    }
     default:
         return fail(ctx, B200R_EINVAL, "render mode not implemented on the device yet");
     }
@@ -164,6 +226,8 @@ int b200r_init(int device, b200r_ctx** out)
     CU(cudaMalloc((void**)&ctx->d_tileCounter, 64));
     CU(cudaMalloc((void**)&ctx->d_ctr, sizeof(DeviceCounters)));
     CU(cudaMemset(ctx->d_ctr, 0, sizeof(DeviceCounters)));
+    CU(cudaMalloc((void**)&ctx->rb.spanCount, 64));
+    CU(cudaMallocHost((void**)&ctx->h_spanCount, 64));
     *out = ctx;
     return B200R_OK;
 }
@@ -175,6 +239,8 @@ void b200r_destroy(b200r_ctx* ctx)
     cudaFree(ctx->d_nodes); cudaFree(ctx->d_leaftris); cudaFree(ctx->d_shade); cudaFree(ctx->d_rverts); cudaFree(ctx->d_rtris);
     for (int i = 0; i < B200R_MAX_LIGHTS; i++) cudaFree(ctx->d_shadowmap[i]);
     cudaFree(ctx->d_frame); cudaFree(ctx->d_tileCounter); cudaFree(ctx->d_ctr);
+    cudaFree(ctx->d_tileProf); cudaFree(ctx->rb.spans); cudaFree(ctx->rb.spanCount); cudaFree(ctx->rb.zkeys); cudaFree(ctx->d_shadowKeys);
+    if (ctx->h_spanCount) cudaFreeHost(ctx->h_spanCount);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -221,7 +287,7 @@ int b200r_upload_scene(b200r_ctx* ctx, const b200r_vertex* verts, uint32_t n_ver
         std::vector<uint32_t> inner_id(n_nodes, 0xFFFFFFFFu);
         uint32_t n_inner = 0;
         for (uint32_t i = 0; i < n_nodes; i++) if (!(nodes[i].a & 0x80000000u)) inner_id[i] = n_inner++;
-        if (n_inner >= 0x80000000u || n_tri_idx >= 0x3fffffffu) return fail(ctx, B200R_EINVAL, "scene too large");
+        if (n_inner >= 0x40000000u || n_tri_idx >= 0x3fffffffu) return fail(ctx, B200R_EINVAL, "scene too large");
         auto ref_of = [&](uint32_t i) -> uint32_t {
             if (!(nodes[i].a & 0x80000000u)) return inner_id[i];
             return (nodes[i].a & 0x7fffffffu) ? (0x80000000u | nodes[i].b) : 0xFFFFFFFFu;
@@ -304,8 +370,20 @@ int b200r_upload_shadowmap(b200r_ctx* ctx, int light, const float* map)
     return B200R_OK;
 }
 
-int b200r_render_shadowmap(b200r_ctx* ctx, int, const float*, const float*)
-{ return fail(ctx, B200R_EINVAL, "b200r_render_shadowmap: not implemented yet"); }
+int b200r_render_shadowmap(b200r_ctx* ctx, int light, const float light_pos[3], const float world2light[9])
+{
+    if (!ctx || !light_pos || !world2light || light < 0 || light >= B200R_MAX_LIGHTS)
+        return fail(ctx, B200R_EINVAL, "bad shadow map argument");
+    if (!ctx->have_scene) return fail(ctx, B200R_ESTATE, "b200r_render_shadowmap before b200r_upload_scene");
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)B200R_SHADOWMAP_SIZE * B200R_SHADOWMAP_SIZE;
+    if (!ctx->d_shadowmap[light]) CU(cudaMalloc((void**)&ctx->d_shadowmap[light], n * 4));
+    if (!ctx->d_shadowKeys) CU(cudaMalloc((void**)&ctx->d_shadowKeys, n * 4));
+    CU(launch_shadowmap(ctx->sc, light_pos, world2light, ctx->d_shadowKeys, ctx->d_shadowmap[light], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->sc.shadowmap[light] = ctx->d_shadowmap[light];
+    return B200R_OK;
+}
 
 int b200r_download_shadowmap(b200r_ctx* ctx, int light, float* map)
 {
@@ -390,6 +468,24 @@ int b200r_selftest_division(b200r_ctx* ctx, uint64_t samples, uint32_t seed, uin
     cudaFree(d_m); cudaFree(d_f);
     *mismatches = m;
     if (first_bad) memcpy(first_bad, fb, 16);
+    return B200R_OK;
+}
+
+int b200r_set_tile_profile(b200r_ctx* ctx, int enabled)
+{
+    if (!ctx) return fail(nullptr, B200R_EINVAL, "NULL ctx");
+    ctx->tileProfile = enabled != 0;
+    return B200R_OK;
+}
+
+int b200r_get_tile_profile(b200r_ctx* ctx, uint64_t* start_end_ns, uint32_t max_tiles, uint32_t* n_tiles)
+{
+    if (!ctx || !n_tiles) return fail(ctx, B200R_EINVAL, "NULL argument");
+    *n_tiles = ctx->lastTiles;
+    if (!start_end_ns || !ctx->d_tileProf) return B200R_OK;
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t n = ctx->lastTiles < max_tiles ? ctx->lastTiles : max_tiles;
+    CU(cudaMemcpy(start_end_ns, ctx->d_tileProf, (size_t)n * 16, cudaMemcpyDeviceToHost));
     return B200R_OK;
 }
 

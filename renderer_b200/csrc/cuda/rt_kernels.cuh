@@ -5,8 +5,19 @@
 namespace b200r {
 
 cudaError_t launch_raytrace(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, unsigned* d_tileCounter,
-                            DeviceCounters* d_ctr, bool count, int numSMs, cudaStream_t stream);
+                            DeviceCounters* d_ctr, bool count, unsigned long long* d_tileProf, int numSMs, cudaStream_t stream);
 
+// Scratch of the rasteriser: span records (80 B each), their count, and the 64-bit depth keys (one per pixel).
+struct RasterBuffers {
+    uint32_t* spans = nullptr;
+    unsigned* spanCount = nullptr;
+    unsigned spanCapacity = 0;
+    unsigned long long* zkeys = nullptr;
+};
+cudaError_t launch_raster(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, RasterBuffers& rb,
+                          DeviceCounters* d_ctr, bool count, int numSMs, cudaStream_t st, int& launches);
+cudaError_t launch_shadowmap(const DeviceScene& sc, const float light_pos[3], const float world2light[9], unsigned* d_keys,
+                             float* d_map, cudaStream_t st);
 cudaError_t launch_division_selftest(unsigned long long samples, uint32_t seed, unsigned long long* d_mismatches,
                                      float* d_firstBad, int numSMs, cudaStream_t stream);
 cudaError_t launch_deinterleave(const uint32_t* gathered, uint32_t* frame, uint32_t W, uint32_t H, uint32_t P,
