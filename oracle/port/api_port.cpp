@@ -29,7 +29,7 @@ int32_t oracle_ao_draw(uint32_t key, uint32_t n)
 
 int oracle_supports(int mode, int mlaa)
 {
-    if (mlaa) return 0;
+    (void)mlaa;     // the MLAA post filter is restated (mlaa_port.cpp) and applies to every supported mode
     return mode == B200R_MODE_RAYTRACE || mode == B200R_MODE_RAYTRACE_AA || mode == B200R_MODE_POINTS ||
            mode == B200R_MODE_POINTS_TRI || (mode >= B200R_MODE_AMBIENT && mode <= B200R_MODE_PHONG_SOFTSHADOWMAPS);
 }
@@ -59,10 +59,14 @@ int oracle_render(const oracle_scene* s, const b200r_frame* f, uint32_t* out, b2
     default:
         return -2;
     }
+    // Screen::ShowScreen (reference src/Screen.h:130-137): MLAA over the finished frame when built --enable-mlaa
+    if ((f->flags & B200R_F_MLAA) && (f->row_step <= 1)) {
+        int rc = oracle_mlaa(out, (int)f->width, (int)f->height);
+        if (rc) return rc;
+    }
     return 0;
 }
 
 }  // extern "C"
 
 // (raster / shadow-map / MLAA restatements live in raster_port.cpp / mlaa_port.cpp)
-extern "C" __attribute__((weak)) int oracle_mlaa(uint32_t*, int, int) { return -3; }

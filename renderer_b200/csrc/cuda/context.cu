@@ -42,6 +42,7 @@ struct b200r_ctx {
     unsigned* h_spanCount = nullptr;          // pinned
     unsigned long long* d_tileProf = nullptr; size_t tileProfTiles = 0; bool tileProfile = false; uint32_t lastTiles = 0;
     unsigned* d_shadowKeys = nullptr;
+    uint32_t* d_mlaaScratch = nullptr; size_t mlaaWords = 0;
     bool counting = false;
     float last_total_ms = 0.f, last_dominant_ms = 0.f;
     uint32_t last_launches = 0;
@@ -113,6 +114,23 @@ int ensure_frame(b200r_ctx* ctx, size_t words)
         CU(cudaMalloc((void**)&ctx->d_frame, words * 4));
         ctx->frame_words = words;
     }
+    return B200R_OK;
+}
+
+int mlaa_on(b200r_ctx* ctx, uint32_t* d_frame, uint32_t width, uint32_t height, cudaStream_t s)
+{
+    if ((width % 4) || (height % 8))
+        return fail(ctx, B200R_EINVAL, "MLAA needs width % 4 == 0 and height % 8 == 0 (the reference's SSE code assumes it, MLAA.cc:396,453)");
+    const size_t words = (size_t)width * height;
+    if (ctx->mlaaWords < words) {
+        if (ctx->d_mlaaScratch) cudaFree(ctx->d_mlaaScratch);
+        ctx->d_mlaaScratch = nullptr; ctx->mlaaWords = 0;
+        CU(cudaMalloc((void**)&ctx->d_mlaaScratch, words * 4));
+        ctx->mlaaWords = words;
+    }
+    int launches = 0;
+    CU(launch_mlaa(d_frame, ctx->d_mlaaScratch, (int)width, (int)height, ctx->numSMs, s, launches));
+    ctx->last_launches += (uint32_t)launches;
     return B200R_OK;
 }
 
@@ -191,6 +209,12 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
     default:
         return fail(ctx, B200R_EINVAL, "render mode not implemented on the device yet");
     }
+    // Screen::ShowScreen's hook (reference src/Screen.h:130-137): MLAA over the finished frame. A row-sharded frame is
+    // filtered after the all-gather instead (b200r_mlaa_device), because the filter needs the neighbouring rows.
+    if ((fp.flags & B200R_F_MLAA) && fp.row_step == 1) {
+        int rc2 = mlaa_on(ctx, d_out, fp.W, fp.H, stream);
+        if (rc2) return rc2;
+    }
     CU(cudaEventRecord(ctx->ev1, stream));
     return B200R_OK;
 }
@@ -239,7 +263,7 @@ void b200r_destroy(b200r_ctx* ctx)
     cudaFree(ctx->d_nodes); cudaFree(ctx->d_leaftris); cudaFree(ctx->d_shade); cudaFree(ctx->d_rverts); cudaFree(ctx->d_rtris);
     for (int i = 0; i < B200R_MAX_LIGHTS; i++) cudaFree(ctx->d_shadowmap[i]);
     cudaFree(ctx->d_frame); cudaFree(ctx->d_tileCounter); cudaFree(ctx->d_ctr);
-    cudaFree(ctx->d_tileProf); cudaFree(ctx->rb.spans); cudaFree(ctx->rb.spanCount); cudaFree(ctx->rb.zkeys); cudaFree(ctx->d_shadowKeys);
+    cudaFree(ctx->d_mlaaScratch); cudaFree(ctx->d_tileProf); cudaFree(ctx->rb.spans); cudaFree(ctx->rb.spanCount); cudaFree(ctx->rb.zkeys); cudaFree(ctx->d_shadowKeys);
     if (ctx->h_spanCount) cudaFreeHost(ctx->h_spanCount);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -438,8 +462,16 @@ int b200r_render(b200r_ctx* ctx, const b200r_frame* f, uint32_t* host_xrgb)
     return B200R_OK;
 }
 
-int b200r_mlaa_device(b200r_ctx* ctx, void*, uint32_t, uint32_t, void*)
-{ return fail(ctx, B200R_EINVAL, "b200r_mlaa_device: not implemented yet"); }
+int b200r_mlaa_device(b200r_ctx* ctx, void* dev_xrgb, uint32_t width, uint32_t height, void* cuda_stream)
+{
+    if (!ctx || !dev_xrgb || !width || !height) return fail(ctx, B200R_EINVAL, "b200r_mlaa_device: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    int rc = mlaa_on(ctx, (uint32_t*)dev_xrgb, width, height, s);
+    if (rc) return rc;
+    if (!cuda_stream) CU(cudaStreamSynchronize(s));
+    return B200R_OK;
+}
 
 int b200r_deinterleave_device(b200r_ctx* ctx, const void* dev_gathered, void* dev_frame, uint32_t width,
                               uint32_t height, uint32_t n_shards, void* cuda_stream)

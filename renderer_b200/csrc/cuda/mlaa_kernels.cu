@@ -1,0 +1,249 @@
+// mlaa_kernels.cu — the reference's morphological anti-aliasing post filter (Intel MLAA 2009) on the device.
+//
+// Replaces MLAA(fbi, NULL, resX, resY) as called single-threaded from Screen::ShowScreen
+// (reference src/Screen.h:133-134, src/MLAA.cc:374-714):
+//   pass "find fragments" (MLAA.cc:437-503): H/V discontinuity flags into bits 31/30 of a scratch copy
+//   blending (MLAA.cc:524-704): horizontal separation lines in 8-row blocks (even blocks, then odd blocks), then
+//   vertical lines in 8-column blocks (even, odd); blending is IN PLACE on the frame, rows inside a block in order.
+// What is parallel here and why it is still bit-identical to the serial job order of the reference:
+//   * blocks of the same parity touch disjoint rows (block b reads/writes rows 8b..8b+8)        -> one CTA per block
+//   * inside a block the 8 rows stay sequential (row y blends into row y+1)                      -> __syncthreads between rows
+//   * separation lines of one row cover disjoint pixel ranges and only read/write inside them    -> one thread per line
+//   * all decisions (flags, split heights) read the immutable scratch copy only.
+// Float maths as in the reference (mixColor's float products + x86 byte truncation), -fmad=false.
+#include "device_types.cuh"
+#include "rt_kernels.cuh"
+
+namespace b200r {
+namespace {
+
+constexpr unsigned HF = 1u << 31, VF = 1u << 30;
+
+// ssedif (MLAA.cc:47-55): some byte differs by >= 16
+__device__ __forceinline__ bool differs(unsigned a, unsigned b)
+{
+    const unsigned d = __vabsdiffu4(a, b);
+    return (d & 0xF0F0F0F0u) != 0;
+}
+
+__device__ __forceinline__ int sumColor(unsigned c) { return (int)((c >> 16) & 0xff) + (int)((c >> 8) & 0xff) + (int)(c & 0xff); }
+
+__device__ __forceinline__ unsigned mixColor(float w1, unsigned c1, float w2, unsigned c2)
+{
+    const float r1 = (float)((c1 >> 16) & 0xff), g1 = (float)((c1 >> 8) & 0xff), b1 = (float)(c1 & 0xff);
+    const float r2 = (float)((c2 >> 16) & 0xff), g2 = (float)((c2 >> 8) & 0xff), b2 = (float)(c2 & 0xff);
+    const unsigned r = u8_x86(r1 * w1 + r2 * w2), g = u8_x86(g1 * w1 + g2 * w2), b = u8_x86(b1 * w1 + b2 * w2);
+    return (r << 16) | (g << 8) | b;
+}
+
+__global__ void mlaa_find_fragments_kernel(const uint32_t* __restrict__ fbi, uint32_t* __restrict__ fb0, int resX, int resY)
+{
+    const size_t n = (size_t)resX * resY;
+    for (size_t ci = (size_t)blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(ci / resX), x = (int)(ci % resX);
+        const unsigned c = fbi[ci];
+        const unsigned below = (y == resY - 1) ? c : fbi[ci + resX];
+        const unsigned right = (x == resX - 1) ? c : fbi[ci + 1];
+        fb0[ci] = c | (differs(c, below) ? HF : 0u) | (differs(c, right) ? VF : 0u);
+    }
+}
+
+__device__ __forceinline__ float getSplitHeight(const uint32_t* __restrict__ fb, int l, int icb, int icm, int ipb, int ipm)
+{
+    const int cc = sumColor(fb[icb]), cu = sumColor(fb[icm]), pc = sumColor(fb[ipb]), pu = sumColor(fb[ipm]);
+    return (float)(l * (pc - cu) + (cc - cu) - (pc - pu)) / (float)(l * ((cc - cu) + (pc - pu)) + (cc - cu) - (pc - pu));
+}
+
+__device__ void computeUpperBounds(int& s0, int& s1, float& h0, float& h1, const uint32_t* __restrict__ fb0, unsigned fc,
+                                   int x0, int x1, int len, int stepx, int befor, int after, int sz)
+{
+    s0 = s1 = -1;
+    int nsteps = 0, xi = x0, t0 = -1, t1 = -1;
+    const unsigned fo = fc ^ (HF | VF);
+    do {
+        if ((fb0[xi] & fo) && (fb0[xi + befor] & fc)) {
+            h0 = getSplitHeight(fb0, len - nsteps, xi + stepx, xi + stepx + after, xi + befor, xi);
+            if (0.f < h0 && h0 < 1.f) { s0 = xi + stepx; break; }
+        }
+        if ((fb0[xi] & fo) && t0 == -1) t0 = xi;
+        xi += stepx;
+        nsteps++;
+    } while (xi < x1);
+    if (s0 == -1 && t0 != -1) { h0 = 0.5f; s0 = t0 + stepx; }
+    if (x1 + stepx >= sz) { if (fb0[x1] & fo) t1 = x1; x1 -= stepx; }
+    xi = x1;
+    do {
+        if ((fb0[xi] & fo) && (fb0[xi + stepx + befor] & fc)) {
+            h1 = getSplitHeight(fb0, nsteps, xi + stepx, xi + stepx + befor, xi + after, xi);
+            if (0.f < h1 && h1 < 1.f) { s1 = xi; break; }
+        }
+        if ((fb0[xi] & fo) && t1 == -1) t1 = xi;
+        xi -= stepx;
+        nsteps++;
+    } while (xi > x0);
+    if (s1 == -1 && t1 != -1) { h1 = 0.5f; s1 = t1; }
+}
+
+__device__ void computeLowerBounds(int& s0, int& s1, float& h0, float& h1, const uint32_t* __restrict__ fb0, unsigned fc,
+                                   int x0, int x1, int len, int stepx, int after, int sz)
+{
+    s0 = s1 = -1;
+    int nsteps = 0, xi = x0, t0 = -1, t1 = -1;
+    const unsigned fo = fc ^ (HF | VF);
+    do {
+        const int xia = xi + after;
+        if ((fb0[xia] & fo) && (fb0[xia] & fc)) {
+            if (xia + after < sz) h0 = getSplitHeight(fb0, len - nsteps, xia + stepx, xi + stepx, xia + after, xia);
+            else h0 = 0.5f;
+            if (0.f < h0 && h0 < 1.f) { s0 = xi + stepx; break; }
+        }
+        if ((fb0[xia] & fo) && t0 == -1) t0 = xi;
+        xi += stepx;
+        nsteps++;
+    } while (xi < x1);
+    if (s0 == -1 && t0 != -1) { h0 = 0.5f; s0 = t0 + stepx; }
+    if (x1 + stepx >= sz) { if (fb0[x1] & fo) t1 = x1; x1 -= stepx; }
+    xi = x1;
+    do {
+        const int xia = xi + after;
+        if ((fb0[xia] & fo) && (fb0[xia + stepx] & fo)) {
+            if (xia + after < sz) h1 = getSplitHeight(fb0, nsteps, xia + stepx, xia + after + stepx, xi, xia);
+            else h1 = 0.5f;
+            if (0.f < h1 && h1 < 1.f) { s1 = xi; break; }
+        }
+        if ((fb0[xia] & fo) && t1 == -1) t1 = xi;
+        xi -= stepx;
+        nsteps++;
+    } while (xi > x0);
+    if (s1 == -1 && t1 != -1) { h1 = 0.5f; s1 = t1; }
+}
+
+__device__ void blendInterval(uint32_t* fbi, int x0, int x1, float h0, float h1, int stepx, int other, bool ushape)
+{
+    float dh0 = ((2.f * (1.f - h0)) * (float)stepx) / (float)(x1 - x0 + stepx);
+    float dh1 = ((2.f * (1.f - h1)) * (float)stepx) / (float)(x1 - x0 + stepx);
+    int shift = other < 0 ? -other : 0;
+    x0 += shift; x1 += shift;
+    const int middle = (x0 + x1) / 2;
+    float area = h0 + 0.5f * dh0;
+    if (h0 == 0.f) {
+        x0 += 1 + (x1 - x0) / stepx;
+        area = dh1;
+    } else {
+        do {
+            fbi[x0] = mixColor(area, fbi[x0], 1.f - area, fbi[x0 + other]);
+            area += dh0;
+            x0 += stepx;
+        } while (x0 < middle);
+        if (x0 == middle) {
+            fbi[x0] = mixColor((1.f - dh0 / 8.f), fbi[x0], dh0 / 8.f, fbi[x0 + other]);
+            if (!ushape) fbi[x0 + other] = mixColor(dh1 / 8.f, fbi[x0], (1.f - dh1 / 8.f), fbi[x0 + other]);
+            x0 += stepx;
+            area = dh1;
+        } else {
+            area = 0.5f * dh1;
+        }
+    }
+    if (h1 == 0.f) return;
+    if (ushape) { area = 1.f - area; dh1 = -dh1; }
+    shift = ushape ? 0 : other;
+    do {
+        fbi[x0 + shift] = mixColor(area, fbi[x0], 1.f - area, fbi[x0 + other]);
+        area += dh1;
+        x0 += stepx;
+    } while (x0 <= x1);
+}
+
+__device__ __forceinline__ void blend_one_cell(uint32_t* fbi, int x0, int after)
+{
+    const float weightc = 7.0f / 8;
+    fbi[x0] = mixColor(weightc, fbi[x0], 1.f - weightc, fbi[x0 + after]);
+    fbi[x0 + after] = mixColor(1.f - weightc, fbi[x0], weightc, fbi[x0 + after]);
+}
+
+// One separation line [x0, x1] of row/column yc (the body of the while loop at MLAA.cc:565-699)
+__device__ void process_line(uint32_t* fbi, const uint32_t* __restrict__ fb0, unsigned fc, int yc, int x0, int x1, int len,
+                             int stepx, int befor, int after, int sz)
+{
+    if (len == 1) { blend_one_cell(fbi, x0, after); return; }
+    if (x0 == yc) { x0 += stepx; len--; }
+    int ui0, ui1, li0, li1; float uh0 = 0.f, uh1 = 0.f, lh0 = 0.f, lh1 = 0.f;
+    computeUpperBounds(ui0, ui1, uh0, uh1, fb0, fc, x0 - stepx, x1, len, stepx, befor, after, sz);
+    computeLowerBounds(li0, li1, lh0, lh1, fb0, fc, x0 - stepx, x1, len, stepx, after, sz);
+    bool done = false;
+    if (ui0 != -1 && li1 != -1 && ui0 < li1) { blendInterval(fbi, ui0, li1, uh0, lh1, stepx, after, false); done = true; }
+    if (li0 != -1 && ui1 != -1 && li0 < ui1) { blendInterval(fbi, li0, ui1, lh0, uh1, stepx, befor, false); done = true; }
+    if (!done) {
+        if (ui0 != -1 && ui1 != -1 && ui0 < ui1) blendInterval(fbi, ui0, ui1, uh0, uh1, stepx, after, true);
+        if (li0 != -1 && li1 != -1 && li0 < li1) blendInterval(fbi, li0, li1, lh0, lh1, stepx, befor, true);
+    }
+}
+
+// One blending job = one 8-row (vertical == 0) or 8-column (vertical == 1) block; one CTA per job.
+// `yodd` selects the parity half of the reference's job list (MLAA.cc:545-552).
+__global__ void __launch_bounds__(256)
+mlaa_blend_kernel(uint32_t* fbi, const uint32_t* __restrict__ fb0, int resX, int resY, int vertical, int yodd)
+{
+    const int rows_per_job = 8;
+    unsigned fc; int resx, resy, stepy, stepx;
+    if (!vertical) { fc = HF; resx = resX; resy = resY; stepy = resX; stepx = 1; }
+    else { fc = VF; resx = resY; resy = resX; stepy = 1; stepx = resX; }
+    const int jobindex = (int)blockIdx.x;
+    int yfrst = (2 * jobindex + yodd) * rows_per_job * stepy;
+    int ylast = yfrst + rows_per_job * stepy;
+    if (ylast >= resy * stepy) ylast = resy * stepy - stepy;
+    int befor = yfrst ? -stepy : 0;
+    const int after = stepy;
+    const int sz = resX * resY;
+    __shared__ int s_lastEnd;      // x1 (as a pixel index k along the row) of the right-most line of the current row
+
+    for (int yc = yfrst; yc < ylast; yc += stepy, befor = -stepy) {
+        if (threadIdx.x == 0) s_lastEnd = -1;
+        __syncthreads();
+        // every maximal run of flagged pixels in [yc, xend] is one separation line (findSeparationLine, :122-176)
+        for (int k = (int)threadIdx.x; k < resx; k += (int)blockDim.x) {
+            const int x = yc + k * stepx;
+            if (!(fb0[x] & fc)) continue;
+            if (k > 0 && (fb0[x - stepx] & fc)) continue;          // not the first pixel of its run
+            int k1 = k;
+            while (k1 + 1 < resx && (fb0[yc + (k1 + 1) * stepx] & fc)) k1++;
+            atomicMax(&s_lastEnd, k1);
+            process_line(fbi, fb0, fc, yc, x, yc + k1 * stepx, k1 - k + 1, stepx, befor, after, sz);
+        }
+        __syncthreads();
+        // The SSE scan quirk of the horizontal search (see oracle/port/mlaa_port.cpp): when the last line of the row
+        // ends 2 or 3 pixels before the end of the row, the search for the next line runs into the first four pixels
+        // of the NEXT row and returns a flagged one as a one-pixel line. Applied after all lines of this row.
+        if (!vertical && threadIdx.x == 0) {
+            const int kEnd = s_lastEnd;
+            if (kEnd >= 0 && (kEnd == resx - 4 || kEnd == resx - 3)) {
+                const int base = yc + resx;                       // first pixel of the next row
+                for (int q = 0; q < 4; q++)
+                    if (fb0[base + q] & HF) {
+                        if (base + q + after < sz) blend_one_cell(fbi, base + q, after);   // (the reference would write out of bounds)
+                        break;
+                    }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_mlaa(uint32_t* d_frame, uint32_t* d_scratch, int resX, int resY, int numSMs, cudaStream_t st, int& launches)
+{
+    mlaa_find_fragments_kernel<<<numSMs * 4, 256, 0, st>>>(d_frame, d_scratch, resX, resY);
+    const int n_hscan_jobs = (resY / 8) + ((resY % 8) ? 1 : 0);
+    const int n_vscan_jobs = (resX / 8) + ((resX % 8) ? 1 : 0);
+    // job list halves (MLAA.cc:545-552): the first scanjobs/2 jobs are the even blocks, the rest the odd blocks
+    const int h0 = n_hscan_jobs / 2, h1 = n_hscan_jobs - h0, v0 = n_vscan_jobs / 2, v1 = n_vscan_jobs - v0;
+    if (h0 > 0) mlaa_blend_kernel<<<h0, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 0, 0);
+    if (h1 > 0) mlaa_blend_kernel<<<h1, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 0, 1);
+    if (v0 > 0) mlaa_blend_kernel<<<v0, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 1, 0);
+    if (v1 > 0) mlaa_blend_kernel<<<v1, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 1, 1);
+    launches += 5;
+    return cudaGetLastError();
+}
+
+}  // namespace b200r

@@ -18,6 +18,7 @@ cudaError_t launch_raster(const DeviceScene& sc, const FrameParams& fp, uint32_t
                           DeviceCounters* d_ctr, bool count, int numSMs, cudaStream_t st, int& launches);
 cudaError_t launch_shadowmap(const DeviceScene& sc, const float light_pos[3], const float world2light[9], unsigned* d_keys,
                              float* d_map, cudaStream_t st);
+cudaError_t launch_mlaa(uint32_t* d_frame, uint32_t* d_scratch, int resX, int resY, int numSMs, cudaStream_t st, int& launches);
 cudaError_t launch_division_selftest(unsigned long long samples, uint32_t seed, unsigned long long* d_mismatches,
                                      float* d_firstBad, int numSMs, cudaStream_t stream);
 cudaError_t launch_deinterleave(const uint32_t* gathered, uint32_t* frame, uint32_t W, uint32_t H, uint32_t P,

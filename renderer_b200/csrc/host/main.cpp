@@ -1,0 +1,164 @@
+// main.cpp — the host program: same command line and main loop as the reference's renderer
+// (reference src/renderer.cc:168-642), with the render call going through the C-ABI to the B200 kernels.
+//
+//   b200renderer [-h] [-r] [-b] [-n N] [-w] [-m mode] [extra long options] FILENAME
+//
+// Kept from the reference: -h help, -r fps report every 5 s, -b benchmark N frames (default 100) along the
+// deterministic orbit, -n N, -w second light, -m <mode> (1..9, 0 = anti-aliased ray tracing), default mode 8,
+// the final "Rendering N frames in S seconds. (F fps)" line.  There is no window here (no SDL, no display):
+// without -b the program renders the same orbit until -n frames are done (default 100).
+// New (the reference's compile-time #defines made runtime):
+//   --width W --height H      (reference: WIDTH/HEIGHT in src/Defines.h:26-27, default 800x600)
+//   --no-reflections          (REFLECTIONS, src/Raytracer.cc:67)      --no-shadows (USE_SHADOWS :63)
+//   --ao N                    (AMBIENT_OCCLUSION + AMBIENT_SAMPLES, src/Raytracer.cc:77-79)
+//   --mlaa                    (--enable-mlaa build + Screen::ShowScreen hook, src/Screen.h:130-137)
+//   --dump PREFIX --frames a,b,c   write PREFIX_<frame>.xrgb (raw 0x00RRGGBB words) for the listed frames
+//   --device D
+#include <getopt.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../../include/b200render.h"
+
+static void usage()
+{
+    fprintf(stderr, "%s\n", b200r_version());
+    fprintf(stderr, "Usage: b200renderer [OPTIONS] [FILENAME]\n\n"
+                    "  -h         this help\n"
+                    "  -r         print FPS reports to stdout (every 5 seconds)\n"
+                    "  -b         benchmark rendering of N frames (default: 100)\n"
+                    "  -n N       set number of benchmarking frames\n"
+                    "  -w         use two lights\n"
+                    "  -m <mode>  rendering mode:\n"
+                    "       1 : point mode\n"
+                    "       2 : points based on triangles (culling,color)\n"
+                    "       3 : triangles, wireframe anti-aliased\n"
+                    "       4 : triangles, ambient colors\n"
+                    "       5 : triangles, Gouraud shading, ZBuffer\n"
+                    "       6 : triangles, per-pixel Phong, ZBuffer\n"
+                    "       7 : triangles, per-pixel Phong, ZBuffer, Shadowmaps\n"
+                    "       8 : triangles, per-pixel Phong, ZBuffer, Soft shadowmaps\n"
+                    "       9 : raytracing, with shadows and reflections\n"
+                    "       0 : raytracing, with shadows, reflections and anti-aliasing\n"
+                    "  --width W --height H --no-reflections --no-shadows --ao N --mlaa\n"
+                    "  --dump PREFIX --frames a,b,c --device D\n");
+    exit(0);
+}
+
+static double now_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+int main(int argc, char* argv[])
+{
+    unsigned mode = B200R_MODE_PHONG_SOFTSHADOWMAPS;     // reference default (renderer.cc:177)
+    bool doReports = false, doBenchmark = false, useTwoLights = false;
+    unsigned benchmarkFrames = 100;
+    unsigned W = 800, H = 600, flags = B200R_F_DEFAULT, ao = 0;
+    int device = 0;
+    std::string dumpPrefix;
+    std::set<unsigned> dumpFrames;
+
+    static option longopts[] = {{"width", required_argument, 0, 1000}, {"height", required_argument, 0, 1001},
+                                {"no-reflections", no_argument, 0, 1002}, {"no-shadows", no_argument, 0, 1003},
+                                {"ao", required_argument, 0, 1004}, {"mlaa", no_argument, 0, 1005},
+                                {"dump", required_argument, 0, 1006}, {"frames", required_argument, 0, 1007},
+                                {"device", required_argument, 0, 1008}, {0, 0, 0, 0}};
+    int c;
+    opterr = 0;
+    while ((c = getopt_long(argc, argv, "hbrwn:m:", longopts, nullptr)) != -1) switch (c) {
+        case 'h': usage(); break;
+        case 'm':
+            if (atoi(optarg) == 0) mode = B200R_MODE_RAYTRACE_AA; else mode = (unsigned)atoi(optarg);
+            if (mode > B200R_MODE_RAYTRACE_AA) usage();
+            break;
+        case 'b': doBenchmark = true; break;
+        case 'r': doReports = true; break;
+        case 'w': useTwoLights = true; break;
+        case 'n': benchmarkFrames = (unsigned)atoi(optarg); break;
+        case 1000: W = (unsigned)atoi(optarg); break;
+        case 1001: H = (unsigned)atoi(optarg); break;
+        case 1002: flags &= ~B200R_F_REFLECTIONS; break;
+        case 1003: flags &= ~B200R_F_SHADOWS; break;
+        case 1004: ao = (unsigned)atoi(optarg); if (ao) flags |= B200R_F_AO; break;
+        case 1005: flags |= B200R_F_MLAA; break;
+        case 1006: dumpPrefix = optarg; break;
+        case 1007: { char* p = optarg; while (*p) { dumpFrames.insert((unsigned)strtoul(p, &p, 10)); if (*p == ',') p++; else break; } } break;
+        case 1008: device = atoi(optarg); break;
+        case '?': fprintf(stderr, "No such option (%c)\n", (char)optopt); usage(); break;
+        default: break;
+    }
+    if (optind == argc) usage();
+    const char* fname = argv[optind];
+
+    b200r_scene* scene = nullptr;
+    if (b200r_scene_load(fname, &scene)) { fprintf(stderr, "%s\n", b200r_last_error(nullptr)); return 0; }
+    uint32_t nv = 0, nt = 0;
+    b200r_scene_vertices(scene, &nv); b200r_scene_tris(scene, &nt);
+    printf("Vertexes: %u Triangles: %u\n", nv, nt);
+    const bool raytrace = (mode == B200R_MODE_RAYTRACE || mode == B200R_MODE_RAYTRACE_AA);
+    if (raytrace) {
+        puts("Creating BVH... please wait...");
+        const std::string cache = std::string(fname) + ".bvh";      // same cache file as the reference
+        const double t0 = now_ms();
+        if (b200r_scene_build_bvh(scene, cache.c_str(), 0)) { fprintf(stderr, "%s\n", b200r_last_error(nullptr)); return 1; }
+        printf("BVH ready in %.2f seconds (depth %d)\n", (now_ms() - t0) / 1000., b200r_scene_bvh_depth(scene));
+    }
+
+    b200r_ctx* ctx = nullptr;
+    if (b200r_init(device, &ctx)) { fprintf(stderr, "%s\n", b200r_last_error(nullptr)); return 1; }
+    if (b200r_upload_scene_handle(ctx, scene)) { fprintf(stderr, "%s\n", b200r_last_error(ctx)); return 1; }
+
+    const unsigned nLights = useTwoLights ? 2 : 1;
+    if (mode == B200R_MODE_PHONG_SHADOWMAPS || mode == B200R_MODE_PHONG_SOFTSHADOWMAPS) {
+        // pLight->RenderSceneIntoShadowBuffer(scene) before the loop (renderer.cc:320,325); the light never moves here
+        for (unsigned i = 0; i < nLights; i++) {
+            float lp[3], w2l[9];
+            b200r_default_light_pos((int)i, lp);
+            b200r_light_world_to_light(lp, w2l);
+            if (b200r_render_shadowmap(ctx, (int)i, lp, w2l)) { fprintf(stderr, "%s\n", b200r_last_error(ctx)); return 1; }
+        }
+    }
+
+    std::vector<uint32_t> fb((size_t)W * H);
+    b200r_orbit orbit; b200r_orbit_init(&orbit);
+    unsigned framesDrawn = 0;
+    double msSpentDrawing = 0, lastReport = now_ms();
+    (void)doBenchmark;      // with no window/keyboard, every run follows the benchmark orbit
+    while (framesDrawn != benchmarkFrames) {
+        float eye[3], mv[9];
+        b200r_orbit_step(&orbit, eye, mv);
+        b200r_frame f;
+        b200r_frame_defaults(&f, mode, W, H, eye, mv, nLights);
+        f.flags = flags; if (ao) f.ao_samples = ao; f.frame_index = framesDrawn;
+        const double t0 = now_ms();
+        if (b200r_render(ctx, &f, fb.data())) { fprintf(stderr, "%s\n", b200r_last_error(ctx)); return 1; }
+        msSpentDrawing += now_ms() - t0;
+        if (!dumpPrefix.empty() && (dumpFrames.empty() || dumpFrames.count(framesDrawn))) {
+            const std::string name = dumpPrefix + "_" + std::to_string(framesDrawn) + ".xrgb";
+            FILE* fp = fopen(name.c_str(), "wb");
+            if (!fp) { perror(name.c_str()); return 2; }
+            fwrite(fb.data(), 4, fb.size(), fp);
+            fclose(fp);
+        }
+        framesDrawn++;
+        if (doReports && now_ms() - lastReport > 5000) {
+            lastReport = now_ms();
+            if (msSpentDrawing > 0) printf("FPS: %g\n", framesDrawn / (msSpentDrawing / 1000.0));
+        }
+    }
+    if (msSpentDrawing > 0)
+        printf("Rendering %u frames in %g seconds. (%g fps)\n", framesDrawn, msSpentDrawing / 1000.0,
+               framesDrawn / (msSpentDrawing / 1000.0));
+    b200r_destroy(ctx);
+    b200r_scene_free(scene);
+    return 0;
+}
