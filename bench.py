@@ -374,7 +374,8 @@ def run_b200_arm(args, wl):
                        "parallelism": "1 GPU" if P == 1 else f"row-cyclic sharding over {P} GPUs + 1 NCCL all-gather + de-interleave",
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "rt_frame_kernel", "kernel_ms": kern_total_ms / K,
+                         "traffic": traffic, "kernel": "ray-tracing step = rt_rootcull + rt_primary (dominant) + rt_shade kernels",
+                         "kernel_ms": kern_total_ms / K,
                          "algorithmic_bytes_per_launch": alg_bytes / K, "peak_source": peak_src + " (of measured)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "fps": K / e2e_s,

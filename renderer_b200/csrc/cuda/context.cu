@@ -4,6 +4,7 @@
 // (reference src/renderer.cc:522-583). There is deliberately NO CPU rendering path in this library:
 // if CUDA is unavailable b200r_init() fails and nothing can be rendered.
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -38,6 +39,7 @@ struct b200r_ctx {
     unsigned* d_tileCounter = nullptr;
     DeviceCounters* d_ctr = nullptr;
     RasterBuffers rb{};
+    RtBuffers rt{};
     size_t zkey_pixels = 0;
     unsigned* h_spanCount = nullptr;          // pinned
     unsigned long long* d_tileProf = nullptr; size_t tileProfTiles = 0; bool tileProfile = false; uint32_t lastTiles = 0;
@@ -158,9 +160,21 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
                 }
                 prof = ctx->d_tileProf; ctx->lastTiles = nTiles;
             }
-            CU(launch_raytrace(ctx->sc, fp, d_out, ctx->d_tileCounter, ctx->d_ctr, ctx->counting, prof, ctx->numSMs, stream));
+            const size_t px32 = (size_t)nTiles * 32;
+            if (ctx->rt.pixels < px32) {
+                if (ctx->rt.queue) cudaFree(ctx->rt.queue);
+                if (ctx->rt.hits) cudaFree(ctx->rt.hits);
+                ctx->rt.queue = nullptr; ctx->rt.hits = nullptr; ctx->rt.pixels = 0;
+                CU(cudaMalloc((void**)&ctx->rt.queue, px32 * 4));
+                CU(cudaMalloc((void**)&ctx->rt.hits, px32 * 32));
+                ctx->rt.pixels = px32;
+            }
+            ctx->rt.counters = ctx->d_tileCounter;
+            ctx->rt.forceMonolithic = getenv("B200R_MONOLITHIC_RT") != nullptr;
+            int launches = 0;
+            CU(launch_raytrace(ctx->sc, fp, d_out, ctx->rt, ctx->d_ctr, ctx->counting, prof, ctx->numSMs, stream, launches));
+            ctx->last_launches += (uint32_t)launches;
         }
-        ctx->last_launches += 1;
         break;
     case B200R_MODE_PHONG_SHADOWMAPS:
     case B200R_MODE_PHONG_SOFTSHADOWMAPS:
@@ -263,7 +277,7 @@ void b200r_destroy(b200r_ctx* ctx)
     cudaFree(ctx->d_nodes); cudaFree(ctx->d_leaftris); cudaFree(ctx->d_shade); cudaFree(ctx->d_rverts); cudaFree(ctx->d_rtris);
     for (int i = 0; i < B200R_MAX_LIGHTS; i++) cudaFree(ctx->d_shadowmap[i]);
     cudaFree(ctx->d_frame); cudaFree(ctx->d_tileCounter); cudaFree(ctx->d_ctr);
-    cudaFree(ctx->d_mlaaScratch); cudaFree(ctx->d_tileProf); cudaFree(ctx->rb.spans); cudaFree(ctx->rb.spanCount); cudaFree(ctx->rb.zkeys); cudaFree(ctx->d_shadowKeys);
+    cudaFree(ctx->rt.queue); cudaFree(ctx->rt.hits); cudaFree(ctx->d_mlaaScratch); cudaFree(ctx->d_tileProf); cudaFree(ctx->rb.spans); cudaFree(ctx->rb.spanCount); cudaFree(ctx->rb.zkeys); cudaFree(ctx->d_shadowKeys);
     if (ctx->h_spanCount) cudaFreeHost(ctx->h_spanCount);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);

@@ -4,8 +4,18 @@
 
 namespace b200r {
 
-cudaError_t launch_raytrace(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, unsigned* d_tileCounter,
-                            DeviceCounters* d_ctr, bool count, unsigned long long* d_tileProf, int numSMs, cudaStream_t stream);
+// Scratch of the ray tracer: `counters` = {tile counter / queue head, root-survivor count, hit count, spare};
+// `queue` = pixel ids whose primary ray enters the root box (<= one per pixel); `hits` = 32-byte hit records.
+struct RtBuffers {
+    unsigned* counters = nullptr;
+    int* queue = nullptr;
+    void* hits = nullptr;
+    size_t pixels = 0;
+    bool forceMonolithic = false;
+};
+cudaError_t launch_raytrace(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, RtBuffers& rt,
+                            DeviceCounters* d_ctr, bool count, unsigned long long* d_tileProf, int numSMs, cudaStream_t stream,
+                            int& launches);
 
 // Scratch of the rasteriser: span records (80 B each), their count, and the 64-bit depth keys (one per pixel).
 struct RasterBuffers {

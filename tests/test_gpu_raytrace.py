@@ -73,3 +73,22 @@ def test_row_sharding_matches_full_frame(rb, load_scene, gpu):
     for r in range(P):
         part = gpu.render(rb.make_frame(rb.MODE_RAYTRACE, W, H, cam, row_first=r, row_step=P))
         assert np.array_equal(part, full[r::P])
+
+
+def test_split_pipeline_equals_monolithic_kernel(rb, load_scene, gpu, monkeypatch):
+    """Mode 9 runs as root-cull -> persistent primary traversal -> shade; the single persistent kernel (used for
+    mode 0) must give the same frame and the same work counters."""
+    import numpy as np
+    s = load_scene("chessboard.tri")
+    gpu.upload(s)
+    cam = rb.Orbit.cameras([40])[40]
+    f = rb.make_frame(rb.MODE_RAYTRACE, 640, 360, cam)
+    gpu.set_counters(True)
+    try:
+        a = gpu.render(f); ca = gpu.counters()
+        monkeypatch.setenv("B200R_MONOLITHIC_RT", "1")
+        b = gpu.render(f); cb = gpu.counters()
+    finally:
+        gpu.set_counters(False)
+    assert np.array_equal(a, b)
+    assert ca == cb

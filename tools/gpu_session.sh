@@ -11,6 +11,6 @@ python bench.py --workload $WL --steps 100 --warmup 5 > gpurun_out/${TAG}_bench_
 python tools/tile_profile.py $WL > gpurun_out/${TAG}_tiles_${WL}.json 2>&1; cat gpurun_out/${TAG}_tiles_${WL}.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_${WL}.csv \
     python bench.py --workload $WL --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:rt_frame_kernel -s 6 -c 2 -f -o gpurun_out/${TAG}_prof_${WL} \
+ncu --set full --clock-control none --import-source on -k regex:rt_primary_kernel -s 4 -c 2 -f -o gpurun_out/${TAG}_prof_${WL} \
     python bench.py --workload $WL --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1
 ls -la gpurun_out | tail -20
