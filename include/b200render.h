@@ -194,6 +194,9 @@ const b200r_tri*     b200r_scene_tris(const b200r_scene* s, uint32_t* n);
 const b200r_bvhnode* b200r_scene_nodes(const b200r_scene* s, uint32_t* n);
 const int32_t*       b200r_scene_tri_idx(const b200r_scene* s, uint32_t* n);
 int                  b200r_scene_bvh_depth(const b200r_scene* s);
+/* Number of triangles whose precomputed edge planes do NOT bound the triangle to within `tol` (fp64 check). The ray
+ * tracer prunes subtrees by distance only for scenes where this is 0 at tol = 2e-5 (DESIGN.md "distance pruning"). */
+uint32_t             b200r_scene_unbounded_triangles(const b200r_scene* s, double tol);
 int  b200r_upload_scene_handle(b200r_ctx* ctx, const b200r_scene* s);   /* convenience */
 
 /* Camera::set + UpdateMV (src/Camera.cc:24-42). */

@@ -85,6 +85,7 @@ SYMBOLS = {
     "b200r_scene_nodes": (P(BvhNode), [C.c_void_p, P(C.c_uint32)]),
     "b200r_scene_tri_idx": (P(C.c_int32), [C.c_void_p, P(C.c_uint32)]),
     "b200r_scene_bvh_depth": (C.c_int, [C.c_void_p]),
+    "b200r_scene_unbounded_triangles": (C.c_uint32, [C.c_void_p, C.c_double]),
     "b200r_upload_scene_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200r_camera_look_at": (None, [P(C.c_float), P(C.c_float), P(C.c_float)]),
     "b200r_orbit_init": (None, [P(Orbit)]),

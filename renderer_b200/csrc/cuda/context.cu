@@ -3,6 +3,7 @@
 // b200r_render() stands where main()'s switch(mode) calls scene.renderXxx(sony, canvas)
 // (reference src/renderer.cc:522-583). There is deliberately NO CPU rendering path in this library:
 // if CUDA is unavailable b200r_init() fails and nothing can be rendered.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstdio>
@@ -16,6 +17,8 @@
 namespace b200r {
 void set_global_error(const std::string& s);
 const char* global_error();
+uint32_t count_unbounded_triangles(const b200r_vertex* verts, uint32_t n_verts, const b200r_tri* tris, uint32_t n_tris, double tol,
+                                   unsigned char* bad_out);
 }
 
 using namespace b200r;
@@ -171,6 +174,7 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
             }
             ctx->rt.counters = ctx->d_tileCounter;
             ctx->rt.forceMonolithic = getenv("B200R_MONOLITHIC_RT") != nullptr;
+            ctx->rt.noPrune = getenv("B200R_NO_PRUNE") != nullptr;
             int launches = 0;
             CU(launch_raytrace(ctx->sc, fp, d_out, ctx->rt, ctx->d_ctr, ctx->counting, prof, ctx->numSMs, stream, launches));
             ctx->last_launches += (uint32_t)launches;
@@ -317,6 +321,13 @@ int b200r_upload_scene(b200r_ctx* ctx, const b200r_vertex* verts, uint32_t n_ver
             if (tri_idx[i] < 0 || (uint32_t)tri_idx[i] >= n_tris) return fail(ctx, B200R_EINVAL, "tri_idx entry out of range");
     }
 
+    // ---- may the closest-hit kernel prune by distance?  (rt_kernels.cu "Distance pruning"; check in host/edgecheck.cpp)
+    // Triangles that fail the check make every BVH node above them "unprunable" (flag bits in the node record); the
+    // rest of the tree is pruned as usual.
+    std::vector<unsigned char> bad_tri(n_tris, 0);
+    b200r::count_unbounded_triangles(verts, n_verts, tris, n_tris, 2e-5, bad_tri.data());
+    const uint32_t prune_ok = 1;
+
     std::vector<float4> hn, hl, hs, hv, ht;
     uint32_t root_ref = 0xFFFFFFFFu, fast_ok = 1;
     float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
@@ -344,6 +355,25 @@ int b200r_upload_scene(b200r_ctx* ctx, const b200r_vertex* verts, uint32_t n_ver
             rec[1] = make_float4(L.lo[1], L.hi[1], R.lo[1], R.hi[1]);
             rec[2] = make_float4(L.lo[2], L.hi[2], R.lo[2], R.hi[2]);
             rec[3] = make_float4(u2f(ref_of(nodes[i].a)), u2f(ref_of(nodes[i].b)), 0.f, 0.f);
+        }
+        // subtree-contains-an-unbounded-triangle flags: children have larger indices than their parent (DFS pre-order),
+        // so one reverse sweep is a post-order pass
+        {
+            std::vector<unsigned char> sub(n_nodes, 0);
+            for (uint32_t ii = n_nodes; ii-- > 0;) {
+                if (nodes[ii].a & 0x80000000u) {
+                    const uint32_t cnt = nodes[ii].a & 0x7fffffffu;
+                    for (uint32_t k = 0; k < cnt; k++) if (bad_tri[(uint32_t)tri_idx[nodes[ii].b + k]]) sub[ii] = 1;
+                } else {
+                    if (nodes[ii].a <= ii || nodes[ii].b <= ii) { std::fill(sub.begin(), sub.end(), 1); break; }   // not pre-order: be safe
+                    sub[ii] = sub[nodes[ii].a] | sub[nodes[ii].b];
+                }
+            }
+            for (uint32_t ii = 0; ii < n_nodes; ii++) {
+                if (nodes[ii].a & 0x80000000u) continue;
+                const uint32_t fl = (sub[nodes[ii].a] ? 1u : 0u) | (sub[nodes[ii].b] ? 2u : 0u);
+                hn[4 * (size_t)inner_id[ii] + 3].z = u2f(fl);
+            }
         }
         root_ref = ref_of(0);
         for (int c = 0; c < 3; c++) { root_lo[c] = nodes[0].lo[c]; root_hi[c] = nodes[0].hi[c]; }
@@ -390,7 +420,7 @@ int b200r_upload_scene(b200r_ctx* ctx, const b200r_vertex* verts, uint32_t n_ver
     ctx->sc.wnodes = ctx->d_nodes; ctx->sc.leaftris = ctx->d_leaftris; ctx->sc.shade = ctx->d_shade;
     ctx->sc.rverts = ctx->d_rverts; ctx->sc.rtris = ctx->d_rtris;
     ctx->sc.n_nodes = n_nodes; ctx->sc.n_list = n_tri_idx; ctx->sc.n_tris = n_tris; ctx->sc.n_verts = n_verts;
-    ctx->sc.root_ref = root_ref; ctx->sc.fast_div_ok = fast_ok;
+    ctx->sc.root_ref = root_ref; ctx->sc.fast_div_ok = fast_ok; ctx->sc.prune_ok = prune_ok;
     memcpy(ctx->sc.root_lo, root_lo, 12); memcpy(ctx->sc.root_hi, root_hi, 12);
     ctx->have_scene = true; ctx->have_bvh = (nodes && n_nodes);
     return B200R_OK;

@@ -33,6 +33,7 @@ struct DeviceScene {
     uint32_t n_nodes, n_list, n_tris, n_verts;
     uint32_t root_ref;        // ref of the root (inner record 0, or a leaf ref for tiny scenes)
     uint32_t fast_div_ok;     // every node bound is 0 or in [2^-35, 2^50]: precondition of the shared-reciprocal divide
+    uint32_t prune_ok;        // every triangle's edge planes bound it to within 2e-5 (checked in fp64 at upload): distance pruning allowed
     float root_lo[3], root_hi[3];
 };
 

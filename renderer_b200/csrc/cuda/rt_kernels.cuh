@@ -12,6 +12,7 @@ struct RtBuffers {
     void* hits = nullptr;
     size_t pixels = 0;
     bool forceMonolithic = false;
+    bool noPrune = false;
 };
 cudaError_t launch_raytrace(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, RtBuffers& rt,
                             DeviceCounters* d_ctr, bool count, unsigned long long* d_tileProf, int numSMs, cudaStream_t stream,

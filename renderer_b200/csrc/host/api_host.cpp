@@ -9,6 +9,7 @@
 #include "scene.h"
 
 namespace b200r {
+uint32_t count_unbounded_triangles(const b200r_vertex*, uint32_t, const b200r_tri*, uint32_t, double, unsigned char*);
 static std::mutex g_err_mu;
 static std::string g_last_error;
 void set_global_error(const std::string& s) { std::lock_guard<std::mutex> l(g_err_mu); g_last_error = s; }
@@ -62,6 +63,12 @@ const b200r_bvhnode* b200r_scene_nodes(const b200r_scene* s, uint32_t* n)
 const int32_t* b200r_scene_tri_idx(const b200r_scene* s, uint32_t* n)
 { if (n) *n = (uint32_t)s->s.tri_idx.size(); return s->s.tri_idx.data(); }
 int b200r_scene_bvh_depth(const b200r_scene* s) { return s->s.bvh_depth; }
+
+uint32_t b200r_scene_unbounded_triangles(const b200r_scene* s, double tol)
+{
+    return b200r::count_unbounded_triangles(s->s.verts.data(), (uint32_t)s->s.verts.size(), s->s.tris.data(),
+                                            (uint32_t)s->s.tris.size(), tol, nullptr);
+}
 
 }  // extern "C"
 

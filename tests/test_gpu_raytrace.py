@@ -92,3 +92,22 @@ def test_split_pipeline_equals_monolithic_kernel(rb, load_scene, gpu, monkeypatc
         gpu.set_counters(False)
     assert np.array_equal(a, b)
     assert ca == cb
+
+
+@pytest.mark.parametrize("model,size", [("chessboard.tri", (1920, 1080)), ("dragon_vis.ply", (1280, 720)), ("tie.ply", (1280, 720)),
+                                        ("x-wing.ply", (800, 600)), ("kerolamp.ply", (800, 600))])
+def test_distance_pruning_changes_nothing(rb, pyport, load_scene, gpu, monkeypatch, model, size):
+    """Near-first ordering + conservative distance pruning of the primary-ray kernel vs the reference's full traversal:
+    same frame, on scenes that do (chessboard, tie, x-wing, kerolamp) and do not contain triangles flagged unprunable."""
+    import numpy as np
+    s = load_scene(model)
+    gpu.upload(s)
+    for k, cam in rb.Orbit.cameras([0, 57]).items():
+        f = rb.make_frame(rb.MODE_RAYTRACE, size[0], size[1], cam)
+        pruned = gpu.render(f)
+        monkeypatch.setenv("B200R_NO_PRUNE", "1")
+        plain = gpu.render(f)
+        monkeypatch.delenv("B200R_NO_PRUNE")
+        assert np.array_equal(pruned, plain), f"{model} frame {k}"
+        if k == 0:
+            assert_parity(pruned, pyport.render(s, f), f"{model} {size} frame {k}")
