@@ -30,8 +30,7 @@ int32_t oracle_ao_draw(uint32_t key, uint32_t n)
 int oracle_supports(int mode, int mlaa)
 {
     (void)mlaa;     // the MLAA post filter is restated (mlaa_port.cpp) and applies to every supported mode
-    return mode == B200R_MODE_RAYTRACE || mode == B200R_MODE_RAYTRACE_AA || mode == B200R_MODE_POINTS ||
-           mode == B200R_MODE_POINTS_TRI || (mode >= B200R_MODE_AMBIENT && mode <= B200R_MODE_PHONG_SOFTSHADOWMAPS);
+    return mode >= B200R_MODE_POINTS && mode <= B200R_MODE_RAYTRACE_AA;
 }
 
 int oracle_render(const oracle_scene* s, const b200r_frame* f, uint32_t* out, b200r_counters* ctr, int threads)
@@ -55,6 +54,9 @@ int oracle_render(const oracle_scene* s, const b200r_frame* f, uint32_t* out, b2
     case B200R_MODE_GOURAUD:
     case B200R_MODE_PHONG:
         oport::render_raster(s, f, out, ctr, threads);
+        break;
+    case B200R_MODE_LINES:
+        oport::render_wireframe(s, f, out, ctr);
         break;
     default:
         return -2;
