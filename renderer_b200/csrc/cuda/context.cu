@@ -43,6 +43,7 @@ struct b200r_ctx {
     DeviceCounters* d_ctr = nullptr;
     RasterBuffers rb{};
     RtBuffers rt{};
+    WireBuffers wb{};
     size_t zkey_pixels = 0;
     unsigned* h_spanCount = nullptr;          // pinned
     unsigned long long* d_tileProf = nullptr; size_t tileProfTiles = 0; bool tileProfile = false; uint32_t lastTiles = 0;
@@ -175,6 +176,10 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
             ctx->rt.counters = ctx->d_tileCounter;
             ctx->rt.forceMonolithic = getenv("B200R_MONOLITHIC_RT") != nullptr;
             ctx->rt.noPrune = getenv("B200R_NO_PRUNE") != nullptr;
+            if (getenv("B200R_WARP_PROFILE")) {
+                if (!ctx->rt.warpProf) CU(cudaMalloc((void**)&ctx->rt.warpProf, (size_t)65536 * 32));
+                prof = nullptr;
+            } else if (ctx->rt.warpProf) { cudaFree(ctx->rt.warpProf); ctx->rt.warpProf = nullptr; }
             int launches = 0;
             CU(launch_raytrace(ctx->sc, fp, d_out, ctx->rt, ctx->d_ctr, ctx->counting, prof, ctx->numSMs, stream, launches));
             ctx->last_launches += (uint32_t)launches;
@@ -224,8 +229,37 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
         }
         break;
     }
+    case B200R_MODE_LINES: {
+        const size_t px = (size_t)fp.W * fp.n_rows;
+        if (fp.W > 32767 || fp.H > 32767) return fail(ctx, B200R_EINVAL, "mode 3 uses 16-bit screen coordinates (Sint16) like the reference");
+        if (ctx->wb.pixels < px) {
+            cudaFree(ctx->wb.counts); cudaFree(ctx->wb.offsets); cudaFree(ctx->wb.blockSums);
+            ctx->wb.counts = ctx->wb.offsets = ctx->wb.blockSums = nullptr; ctx->wb.pixels = 0;
+            CU(cudaMalloc((void**)&ctx->wb.counts, px * 4));
+            CU(cudaMalloc((void**)&ctx->wb.offsets, (px + 1) * 4));
+            CU(cudaMalloc((void**)&ctx->wb.blockSums, ((px + 1023) / 1024 + 1) * 4));
+            ctx->wb.pixels = px;
+        }
+        if (!ctx->wb.total) CU(cudaMalloc((void**)&ctx->wb.total, 64));
+        int launches = 0;
+        CU(launch_wire_count(ctx->sc, fp, d_out, ctx->wb, stream, launches));
+        // the fragment buffer is sized from the count pass (one small read-back per frame)
+        CU(cudaMemcpyAsync(ctx->h_spanCount, ctx->wb.total, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        const unsigned need = *ctx->h_spanCount;
+        if (need > ctx->wb.capacity) {
+            cudaFree(ctx->wb.frags); ctx->wb.frags = nullptr; ctx->wb.capacity = 0;
+            unsigned cap = 1u << 20;
+            while (cap < need) cap *= 2;
+            CU(cudaMalloc(&ctx->wb.frags, (size_t)cap * 8));
+            ctx->wb.capacity = cap;
+        }
+        CU(launch_wire_emit(ctx->sc, fp, d_out, ctx->wb, ctx->numSMs, stream, launches));
+        ctx->last_launches += (uint32_t)launches;
+        break;
+    }
     default:
-        return fail(ctx, B200R_EINVAL, "render mode not implemented on the device yet");
+        return fail(ctx, B200R_EINVAL, "render mode must be 1..10");
     }
     // Screen::ShowScreen's hook (reference src/Screen.h:130-137): MLAA over the finished frame. A row-sharded frame is
     // filtered after the all-gather instead (b200r_mlaa_device), because the filter needs the neighbouring rows.
@@ -281,6 +315,7 @@ void b200r_destroy(b200r_ctx* ctx)
     cudaFree(ctx->d_nodes); cudaFree(ctx->d_leaftris); cudaFree(ctx->d_shade); cudaFree(ctx->d_rverts); cudaFree(ctx->d_rtris);
     for (int i = 0; i < B200R_MAX_LIGHTS; i++) cudaFree(ctx->d_shadowmap[i]);
     cudaFree(ctx->d_frame); cudaFree(ctx->d_tileCounter); cudaFree(ctx->d_ctr);
+    cudaFree(ctx->wb.counts); cudaFree(ctx->wb.offsets); cudaFree(ctx->wb.blockSums); cudaFree(ctx->wb.total); cudaFree(ctx->wb.frags);
     cudaFree(ctx->rt.queue); cudaFree(ctx->rt.hits); cudaFree(ctx->d_mlaaScratch); cudaFree(ctx->d_tileProf); cudaFree(ctx->rb.spans); cudaFree(ctx->rb.spanCount); cudaFree(ctx->rb.zkeys); cudaFree(ctx->d_shadowKeys);
     if (ctx->h_spanCount) cudaFreeHost(ctx->h_spanCount);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -557,6 +592,14 @@ int b200r_set_tile_profile(b200r_ctx* ctx, int enabled)
 int b200r_get_tile_profile(b200r_ctx* ctx, uint64_t* start_end_ns, uint32_t max_tiles, uint32_t* n_tiles)
 {
     if (!ctx || !n_tiles) return fail(ctx, B200R_EINVAL, "NULL argument");
+    if (ctx->rt.warpProf) {      // B200R_WARP_PROFILE: per-warp records of rt_primary_kernel (2 "tiles" per warp)
+        *n_tiles = ctx->rt.lastPrimaryWarps * 2;
+        if (!start_end_ns) return B200R_OK;
+        CU(cudaSetDevice(ctx->device));
+        const uint32_t n = *n_tiles < max_tiles ? *n_tiles : max_tiles;
+        CU(cudaMemcpy(start_end_ns, ctx->rt.warpProf, (size_t)n * 16, cudaMemcpyDeviceToHost));
+        return B200R_OK;
+    }
     *n_tiles = ctx->lastTiles;
     if (!start_end_ns || !ctx->d_tileProf) return B200R_OK;
     CU(cudaSetDevice(ctx->device));

@@ -13,6 +13,8 @@ struct RtBuffers {
     size_t pixels = 0;
     bool forceMonolithic = false;
     bool noPrune = false;
+    unsigned long long* warpProf = nullptr;   // developer tool (B200R_WARP_PROFILE): 4 x u64 per warp of rt_primary_kernel
+    unsigned lastPrimaryWarps = 0;
 };
 cudaError_t launch_raytrace(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, RtBuffers& rt,
                             DeviceCounters* d_ctr, bool count, unsigned long long* d_tileProf, int numSMs, cudaStream_t stream,
@@ -29,6 +31,14 @@ cudaError_t launch_raster(const DeviceScene& sc, const FrameParams& fp, uint32_t
                           DeviceCounters* d_ctr, bool count, int numSMs, cudaStream_t st, int& launches);
 cudaError_t launch_shadowmap(const DeviceScene& sc, const float light_pos[3], const float world2light[9], unsigned* d_keys,
                              float* d_map, cudaStream_t st);
+// Scratch of mode 3 (wireframe): per-pixel fragment counts / offsets, scan block sums, fragment records (8 B each).
+struct WireBuffers {
+    uint32_t* counts = nullptr; uint32_t* offsets = nullptr; uint32_t* blockSums = nullptr; uint32_t* total = nullptr;
+    void* frags = nullptr; uint32_t capacity = 0; size_t pixels = 0;
+};
+cudaError_t launch_wire_count(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, WireBuffers& wb, cudaStream_t st, int& launches);
+cudaError_t launch_wire_emit(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, WireBuffers& wb, int numSMs, cudaStream_t st,
+                             int& launches);
 cudaError_t launch_mlaa(uint32_t* d_frame, uint32_t* d_scratch, int resX, int resY, int numSMs, cudaStream_t st, int& launches);
 cudaError_t launch_division_selftest(unsigned long long samples, uint32_t seed, unsigned long long* d_mismatches,
                                      float* d_firstBad, int numSMs, cudaStream_t stream);

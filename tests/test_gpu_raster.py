@@ -33,7 +33,7 @@ def test_shadowmap_matches_oracle_bit_for_bit(rb, pyport, load_scene, gpu, model
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"{model} light {li}"
 
 
-@pytest.mark.parametrize("mode", [1, 2, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("model,frame_no,lights", [("statue.ply", 0, 1), ("chessboard.tri", 31, 2), ("trainColor.tri", 5, 1),
                                                    ("dragon_vis.ply", 77, 1)])
 def test_raster_modes_vs_oracle(rb, pyport, load_scene, gpu, mode, model, frame_no, lights):
@@ -47,7 +47,7 @@ def test_raster_modes_vs_oracle(rb, pyport, load_scene, gpu, mode, model, frame_
 
 
 @pytest.mark.parametrize("name", sorted(n for n, c in CASES.items()
-                                        if c["mode"] in (1, 2, 4, 5, 6, 7, 8) and not c["variant"].get("mlaa")))
+                                        if c["mode"] in (1, 2, 3, 4, 5, 6, 7, 8) and not c["variant"].get("mlaa")))
 def test_raster_vs_reference_golden(rb, load_scene, gpu, name):
     c, frames = case_frames(rb, name)
     s = load_scene(c["model"], bvh=False)
@@ -100,3 +100,18 @@ def test_full_size_c4_properties(rb, pyport, load_scene, gpu):
         assert np.array_equal(a, b)
         assert_parity(a, pyport.render(s, f), f"statue 4K mode {mode}")
         assert 0.02 < float((a != 0).mean()) < 0.6
+
+
+@pytest.mark.parametrize("model,size", [("chessboard.tri", (1920, 1080)), ("statue.ply", (1280, 720)), ("torus.ply", (3840, 2160))])
+def test_wireframe_full_size(rb, pyport, load_scene, gpu, model, size):
+    """Mode 3 must be BIT-exact (integer Wu lines + ordered alpha blending), including lines clipped at the borders."""
+    import numpy as np
+    s = load_scene(model, bvh=False)
+    gpu.upload(s)
+    cam = rb.Orbit.cameras([21])[21]
+    f = rb.make_frame(3, size[0], size[1], cam)
+    got = gpu.render(f)
+    assert np.array_equal(got, pyport.render(s, f)), f"{model} {size}"
+    for r in range(2):
+        part = gpu.render(rb.make_frame(3, size[0], size[1], cam, row_first=r, row_step=2))
+        assert np.array_equal(part, got[r::2])
