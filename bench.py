@@ -256,11 +256,12 @@ def run_b200_arm(args, wl):
         """One frame, inputs resident, on torch's current stream. Returns my kernel launches."""
         if P == 1:
             gpu.render_device(frame_for(step), full.data_ptr(), sptr)
-            return 1
+            return gpu.last_launches()
         gpu.render_device(frame_for(step), shard.data_ptr(), sptr)
+        n = gpu.last_launches()
         dist.all_gather_into_tensor(gathered, shard)
         gpu.deinterleave_device(gathered.data_ptr(), full.data_ptr(), W, H, P, sptr)
-        return 2
+        return n + 1
 
     def step_e2e(step):
         """The user-facing call with HOST buffers: per-frame state in (kernel args), frame out to host memory."""
@@ -315,10 +316,10 @@ def run_b200_arm(args, wl):
             ev[i][1].record()
         else:
             gpu.render_device(frame_for(Wm + i), shard.data_ptr(), sptr)
+            launches += gpu.last_launches() + 1
             ev[i][1].record()
             dist.all_gather_into_tensor(gathered, shard)
             gpu.deinterleave_device(gathered.data_ptr(), full.data_ptr(), W, H, P, sptr)
-            launches += 2
         ev[i][2].record()
     barrier()
     wall = time.perf_counter() - t_wall0
@@ -374,7 +375,7 @@ def run_b200_arm(args, wl):
                        "parallelism": "1 GPU" if P == 1 else f"row-cyclic sharding over {P} GPUs + 1 NCCL all-gather + de-interleave",
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "ray-tracing step = rt_rootcull + rt_primary (dominant) + rt_shade kernels",
+                         "traffic": traffic, "kernel": "ray-tracing step = rt_rootcull_kernel + rt_primary_kernel (dominant; shades and casts the shadow rays itself)",
                          "kernel_ms": kern_total_ms / K,
                          "algorithmic_bytes_per_launch": alg_bytes / K, "peak_source": peak_src + " (of measured)"},
             "cpu_baseline": cpu,

@@ -13,6 +13,7 @@ struct RtBuffers {
     size_t pixels = 0;
     bool forceMonolithic = false;
     bool noPrune = false;
+    bool noFuse = false;
     unsigned long long* warpProf = nullptr;   // developer tool (B200R_WARP_PROFILE): 4 x u64 per warp of rt_primary_kernel
     unsigned lastPrimaryWarps = 0;
 };

@@ -111,3 +111,21 @@ def test_distance_pruning_changes_nothing(rb, pyport, load_scene, gpu, monkeypat
         assert np.array_equal(pruned, plain), f"{model} frame {k}"
         if k == 0:
             assert_parity(pruned, pyport.render(s, f), f"{model} {size} frame {k}")
+
+
+@pytest.mark.parametrize("flags", [1 | 4, 4, 1, 0])
+@pytest.mark.parametrize("model", ["chessboard.tri", "dragon_vis.ply", "trainColor.tri"])
+def test_fused_shadow_continuation_equals_split_pipeline(rb, pyport, load_scene, gpu, monkeypatch, model, flags):
+    """One light, no reflections, no AO: primary lanes shade their hit and continue as its shadow ray (no hit queue, no
+    shade kernel). Must equal the split pipeline and the oracle."""
+    import numpy as np
+    s = load_scene(model)
+    gpu.upload(s)
+    cam = rb.Orbit.cameras([33])[33]
+    f = rb.make_frame(rb.MODE_RAYTRACE, 1280, 720, cam, flags=flags)
+    fused = gpu.render(f)
+    monkeypatch.setenv("B200R_NO_FUSE", "1")
+    split = gpu.render(f)
+    monkeypatch.delenv("B200R_NO_FUSE")
+    assert np.array_equal(fused, split)
+    assert_parity(fused, pyport.render(s, f), f"{model} flags={flags} fused")
