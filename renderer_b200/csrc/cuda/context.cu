@@ -166,11 +166,12 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
             }
             const size_t px32 = (size_t)nTiles * 32;
             if (ctx->rt.pixels < px32) {
-                if (ctx->rt.queue) cudaFree(ctx->rt.queue);
-                if (ctx->rt.hits) cudaFree(ctx->rt.hits);
-                ctx->rt.queue = nullptr; ctx->rt.hits = nullptr; ctx->rt.pixels = 0;
-                CU(cudaMalloc((void**)&ctx->rt.queue, px32 * 4));
+                cudaFree(ctx->rt.queue); cudaFree(ctx->rt.hits); cudaFree(ctx->rt.keys); cudaFree(ctx->rt.pend);
+                ctx->rt.queue = nullptr; ctx->rt.hits = nullptr; ctx->rt.keys = nullptr; ctx->rt.pend = nullptr; ctx->rt.pixels = 0;
+                CU(cudaMalloc((void**)&ctx->rt.queue, px32 * 8 * 8));        // <= 8 jobs of 8 bytes per pixel
                 CU(cudaMalloc((void**)&ctx->rt.hits, px32 * 32));
+                CU(cudaMalloc((void**)&ctx->rt.keys, px32 * 8));
+                CU(cudaMalloc((void**)&ctx->rt.pend, px32 * 4));
                 ctx->rt.pixels = px32;
             }
             ctx->rt.counters = ctx->d_tileCounter;

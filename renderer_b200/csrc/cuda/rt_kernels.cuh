@@ -5,10 +5,13 @@
 namespace b200r {
 
 // Scratch of the ray tracer: `counters` = {tile counter / queue head, root-survivor count, hit count, spare};
-// `queue` = pixel ids whose primary ray enters the root box (<= one per pixel); `hits` = 32-byte hit records.
+// `queue` = (pixel, subtree) jobs of the primary rays that enter the root box (<= 8 per pixel); `hits` = 32-byte hit
+// records; `keys`/`pend` = per pixel: best (hitZ, list position) so far and number of jobs still running.
 struct RtBuffers {
     unsigned* counters = nullptr;
-    int* queue = nullptr;
+    void* queue = nullptr;
+    unsigned long long* keys = nullptr;
+    unsigned* pend = nullptr;
     void* hits = nullptr;
     size_t pixels = 0;
     bool forceMonolithic = false;
