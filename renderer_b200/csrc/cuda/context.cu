@@ -178,6 +178,8 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
             ctx->rt.forceMonolithic = getenv("B200R_MONOLITHIC_RT") != nullptr;
             ctx->rt.noPrune = getenv("B200R_NO_PRUNE") != nullptr;
             ctx->rt.noFuse = getenv("B200R_NO_FUSE") != nullptr;
+            ctx->rt.refillBelow = getenv("B200R_REFILL_BELOW") ? atoi(getenv("B200R_REFILL_BELOW")) : 0;
+            ctx->rt.innerBurst = getenv("B200R_INNER_BURST") ? atoi(getenv("B200R_INNER_BURST")) : 0;
             if (getenv("B200R_WARP_PROFILE")) {
                 if (!ctx->rt.warpProf) CU(cudaMalloc((void**)&ctx->rt.warpProf, (size_t)65536 * 32));
                 prof = nullptr;

@@ -17,6 +17,7 @@ struct RtBuffers {
     bool forceMonolithic = false;
     bool noPrune = false;
     bool noFuse = false;
+    int refillBelow = 0, innerBurst = 0;      // tuning overrides (B200R_REFILL_BELOW / B200R_INNER_BURST), 0 = built-in
     unsigned long long* warpProf = nullptr;   // developer tool (B200R_WARP_PROFILE): 4 x u64 per warp of rt_primary_kernel
     unsigned lastPrimaryWarps = 0;
 };
