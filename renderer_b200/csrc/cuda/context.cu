@@ -167,17 +167,26 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
             const size_t px32 = (size_t)nTiles * 32;
             if (ctx->rt.pixels < px32) {
                 cudaFree(ctx->rt.queue); cudaFree(ctx->rt.hits); cudaFree(ctx->rt.keys); cudaFree(ctx->rt.pend);
+    cudaFree(ctx->rt.srays); cudaFree(ctx->rt.sword); cudaFree(ctx->rt.queue2);
                 ctx->rt.queue = nullptr; ctx->rt.hits = nullptr; ctx->rt.keys = nullptr; ctx->rt.pend = nullptr; ctx->rt.pixels = 0;
                 CU(cudaMalloc((void**)&ctx->rt.queue, px32 * 8 * 8));        // <= 8 jobs of 8 bytes per pixel
                 CU(cudaMalloc((void**)&ctx->rt.hits, px32 * 32));
                 CU(cudaMalloc((void**)&ctx->rt.keys, px32 * 8));
+                cudaFree(ctx->rt.srays); cudaFree(ctx->rt.sword); cudaFree(ctx->rt.queue2);
+                ctx->rt.srays = nullptr; ctx->rt.sword = nullptr; ctx->rt.queue2 = nullptr;
+                CU(cudaMalloc((void**)&ctx->rt.srays, px32 * 48));
+                CU(cudaMalloc((void**)&ctx->rt.sword, px32 * 4));
+                CU(cudaMalloc((void**)&ctx->rt.queue2, px32 * 8 * 8));
                 CU(cudaMalloc((void**)&ctx->rt.pend, px32 * 4));
                 ctx->rt.pixels = px32;
             }
             ctx->rt.counters = ctx->d_tileCounter;
             ctx->rt.forceMonolithic = getenv("B200R_MONOLITHIC_RT") != nullptr;
             ctx->rt.noPrune = getenv("B200R_NO_PRUNE") != nullptr;
-            ctx->rt.noFuse = getenv("B200R_NO_FUSE") != nullptr;
+            {
+                const char* pth = getenv("B200R_RT_PATH");       // generic | fused | jobs (default)
+                ctx->rt.fuseMode = (getenv("B200R_NO_FUSE") || (pth && !strcmp(pth, "generic"))) ? 0 : ((pth && !strcmp(pth, "fused")) ? 1 : 2);
+            }
             ctx->rt.refillBelow = getenv("B200R_REFILL_BELOW") ? atoi(getenv("B200R_REFILL_BELOW")) : 0;
             ctx->rt.innerBurst = getenv("B200R_INNER_BURST") ? atoi(getenv("B200R_INNER_BURST")) : 0;
             if (getenv("B200R_WARP_PROFILE")) {

@@ -123,9 +123,11 @@ def test_fused_shadow_continuation_equals_split_pipeline(rb, pyport, load_scene,
     gpu.upload(s)
     cam = rb.Orbit.cameras([33])[33]
     f = rb.make_frame(rb.MODE_RAYTRACE, 1280, 720, cam, flags=flags)
-    fused = gpu.render(f)
-    monkeypatch.setenv("B200R_NO_FUSE", "1")
-    split = gpu.render(f)
-    monkeypatch.delenv("B200R_NO_FUSE")
-    assert np.array_equal(fused, split)
-    assert_parity(fused, pyport.render(s, f), f"{model} flags={flags} fused")
+    jobs = gpu.render(f)                                   # default: shadow rays as (ray, subtree) jobs
+    monkeypatch.setenv("B200R_RT_PATH", "fused")
+    fused = gpu.render(f)                                  # primary lanes continue as their shadow ray
+    monkeypatch.setenv("B200R_RT_PATH", "generic")
+    split = gpu.render(f)                                  # generic shade kernel
+    monkeypatch.delenv("B200R_RT_PATH")
+    assert np.array_equal(jobs, split) and np.array_equal(fused, split)
+    assert_parity(jobs, pyport.render(s, f), f"{model} flags={flags} shadow-job pipeline")
