@@ -167,7 +167,6 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
             const size_t px32 = (size_t)nTiles * 32;
             if (ctx->rt.pixels < px32) {
                 cudaFree(ctx->rt.queue); cudaFree(ctx->rt.hits); cudaFree(ctx->rt.keys); cudaFree(ctx->rt.pend);
-    cudaFree(ctx->rt.srays); cudaFree(ctx->rt.sword); cudaFree(ctx->rt.queue2);
                 ctx->rt.queue = nullptr; ctx->rt.hits = nullptr; ctx->rt.keys = nullptr; ctx->rt.pend = nullptr; ctx->rt.pixels = 0;
                 CU(cudaMalloc((void**)&ctx->rt.queue, px32 * 8 * 8));        // <= 8 jobs of 8 bytes per pixel
                 CU(cudaMalloc((void**)&ctx->rt.hits, px32 * 32));
@@ -184,8 +183,8 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
             ctx->rt.forceMonolithic = getenv("B200R_MONOLITHIC_RT") != nullptr;
             ctx->rt.noPrune = getenv("B200R_NO_PRUNE") != nullptr;
             {
-                const char* pth = getenv("B200R_RT_PATH");       // generic | fused | jobs (default)
-                ctx->rt.fuseMode = (getenv("B200R_NO_FUSE") || (pth && !strcmp(pth, "generic"))) ? 0 : ((pth && !strcmp(pth, "fused")) ? 1 : 2);
+                const char* pth = getenv("B200R_RT_PATH");       // generic | fused (default) | jobs
+                ctx->rt.fuseMode = (getenv("B200R_NO_FUSE") || (pth && !strcmp(pth, "generic"))) ? 0 : ((pth && !strcmp(pth, "jobs")) ? 2 : 1);
             }
             ctx->rt.refillBelow = getenv("B200R_REFILL_BELOW") ? atoi(getenv("B200R_REFILL_BELOW")) : 0;
             ctx->rt.innerBurst = getenv("B200R_INNER_BURST") ? atoi(getenv("B200R_INNER_BURST")) : 0;
@@ -329,7 +328,9 @@ void b200r_destroy(b200r_ctx* ctx)
     for (int i = 0; i < B200R_MAX_LIGHTS; i++) cudaFree(ctx->d_shadowmap[i]);
     cudaFree(ctx->d_frame); cudaFree(ctx->d_tileCounter); cudaFree(ctx->d_ctr);
     cudaFree(ctx->wb.counts); cudaFree(ctx->wb.offsets); cudaFree(ctx->wb.blockSums); cudaFree(ctx->wb.total); cudaFree(ctx->wb.frags);
-    cudaFree(ctx->rt.queue); cudaFree(ctx->rt.hits); cudaFree(ctx->d_mlaaScratch); cudaFree(ctx->d_tileProf); cudaFree(ctx->rb.spans); cudaFree(ctx->rb.spanCount); cudaFree(ctx->rb.zkeys); cudaFree(ctx->d_shadowKeys);
+    cudaFree(ctx->rt.queue); cudaFree(ctx->rt.hits); cudaFree(ctx->rt.keys); cudaFree(ctx->rt.pend);
+    cudaFree(ctx->rt.srays); cudaFree(ctx->rt.sword); cudaFree(ctx->rt.queue2); cudaFree(ctx->rt.warpProf);
+    cudaFree(ctx->d_mlaaScratch); cudaFree(ctx->d_tileProf); cudaFree(ctx->rb.spans); cudaFree(ctx->rb.spanCount); cudaFree(ctx->rb.zkeys); cudaFree(ctx->d_shadowKeys);
     if (ctx->h_spanCount) cudaFreeHost(ctx->h_spanCount);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);

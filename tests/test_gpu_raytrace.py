@@ -123,9 +123,9 @@ def test_fused_shadow_continuation_equals_split_pipeline(rb, pyport, load_scene,
     gpu.upload(s)
     cam = rb.Orbit.cameras([33])[33]
     f = rb.make_frame(rb.MODE_RAYTRACE, 1280, 720, cam, flags=flags)
-    jobs = gpu.render(f)                                   # default: shadow rays as (ray, subtree) jobs
-    monkeypatch.setenv("B200R_RT_PATH", "fused")
-    fused = gpu.render(f)                                  # primary lanes continue as their shadow ray
+    fused = gpu.render(f)                                  # default: primary lanes continue as their shadow ray
+    monkeypatch.setenv("B200R_RT_PATH", "jobs")
+    jobs = gpu.render(f)                                   # shadow rays as (ray, subtree) jobs in a second persistent kernel
     monkeypatch.setenv("B200R_RT_PATH", "generic")
     split = gpu.render(f)                                  # generic shade kernel
     monkeypatch.delenv("B200R_RT_PATH")

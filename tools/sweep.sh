@@ -1,17 +1,14 @@
 #!/bin/bash
-python -m pytest tests/test_gpu_raytrace.py -m gpu -q -x 2>&1 | tail -2
-for P in jobs fused generic; do
-  echo -n "path=$P  "
-  B200R_RT_PATH=$P python bench.py --steps 40 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['ms_per_step'],4), round(d['fps'],1), d['gpu_launches'])"
-done
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/q6_launches.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-python - <<PY
-import csv
-from collections import defaultdict
-rows=list(csv.reader(open("gpurun_out/q6_launches.csv")))
-s=next(i for i,r in enumerate(rows) if r and r[0]=='ID'); h=rows[s]; ki=h.index('Kernel Name'); vi=h.index('Metric Value')
-d=defaultdict(list)
-for r in rows[s+1:]:
-    if len(r)>vi: d[r[ki].split('(')[0][-40:]].append(float(r[vi].replace(',','')))
-for k,v in d.items(): print(k, len(v), 'avg us', round(sum(v)/len(v)/1e3,1))
+CUDA_LAUNCH_BLOCKING=1 python -m pytest tests/test_gpu_raytrace.py -m gpu -q -x -k "split_pipeline" 2>&1 | tail -5
+compute-sanitizer --tool memcheck python - <<PY 2>&1 | tail -30
+import sys; sys.path.insert(0,'.')
+import renderer_b200 as rb
+from oracle import pyport
+p=pyport.model_path('chessboard.tri')
+s=rb.Scene(p).UpdateBoundingVolumeHierarchy(p+'.bvh')
+g=rb.Renderer(0); g.upload(s)
+cam=rb.Orbit.cameras([40])[40]
+f=rb.make_frame(9,640,360,cam)
+g.set_counters(True)
+a=g.render(f); print(g.counters())
 PY
