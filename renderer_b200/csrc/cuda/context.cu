@@ -175,6 +175,9 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
                 ctx->rt.srays = nullptr; ctx->rt.sword = nullptr; ctx->rt.queue2 = nullptr;
                 CU(cudaMalloc((void**)&ctx->rt.srays, px32 * 48));
                 CU(cudaMalloc((void**)&ctx->rt.sword, px32 * 4));
+                cudaFree(ctx->rt.sdon); ctx->rt.sdon = nullptr;
+                CU(cudaMalloc((void**)&ctx->rt.sdon, px32 * 4));
+                CU(cudaMemsetAsync(ctx->rt.sdon, 0, px32 * 4, stream));
                 CU(cudaMalloc((void**)&ctx->rt.queue2, px32 * 8 * 8));
                 CU(cudaMalloc((void**)&ctx->rt.pend, px32 * 4));
                 ctx->rt.pixels = px32;
@@ -329,7 +332,7 @@ void b200r_destroy(b200r_ctx* ctx)
     cudaFree(ctx->d_frame); cudaFree(ctx->d_tileCounter); cudaFree(ctx->d_ctr);
     cudaFree(ctx->wb.counts); cudaFree(ctx->wb.offsets); cudaFree(ctx->wb.blockSums); cudaFree(ctx->wb.total); cudaFree(ctx->wb.frags);
     cudaFree(ctx->rt.queue); cudaFree(ctx->rt.hits); cudaFree(ctx->rt.keys); cudaFree(ctx->rt.pend);
-    cudaFree(ctx->rt.srays); cudaFree(ctx->rt.sword); cudaFree(ctx->rt.queue2); cudaFree(ctx->rt.warpProf);
+    cudaFree(ctx->rt.srays); cudaFree(ctx->rt.sword); cudaFree(ctx->rt.queue2); cudaFree(ctx->rt.warpProf); cudaFree(ctx->rt.sdon);
     cudaFree(ctx->d_mlaaScratch); cudaFree(ctx->d_tileProf); cudaFree(ctx->rb.spans); cudaFree(ctx->rb.spanCount); cudaFree(ctx->rb.zkeys); cudaFree(ctx->d_shadowKeys);
     if (ctx->h_spanCount) cudaFreeHost(ctx->h_spanCount);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);

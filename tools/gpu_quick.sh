@@ -1,16 +1,18 @@
 #!/bin/bash
 # Short GPU-box session: ray-tracing parity subset, bench without the CPU leg, warp profile.
-TAG=${1:-q}; WL=${2:-c2}
+# usage: tools/gpu_quick.sh TAG WORKLOAD [RT_PATH]
+TAG=${1:-q}; WL=${2:-c2}; PTH=${3:-}
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_raytrace.py -m gpu -q -x > gpurun_out/${TAG}_pytest.log 2>&1; tail -3 gpurun_out/${TAG}_pytest.log
-python bench.py --workload $WL --steps 60 --warmup 5 --no-cpu-baseline > gpurun_out/${TAG}_bench_${WL}.json 2> gpurun_out/${TAG}_bench_${WL}.err
+timeout 600 python -m pytest tests/test_gpu_raytrace.py -m gpu -q -x > gpurun_out/${TAG}_pytest.log 2>&1; tail -3 gpurun_out/${TAG}_pytest.log
+[ -n "$PTH" ] && export B200R_RT_PATH=$PTH
+timeout 300 python bench.py --workload $WL --steps 60 --warmup 5 --no-cpu-baseline > gpurun_out/${TAG}_bench_${WL}.json 2> gpurun_out/${TAG}_bench_${WL}.err
 python - <<PY
 import json
 d=json.load(open("gpurun_out/${TAG}_bench_${WL}.json"))
 print({k:d[k] for k in ['value','fps','ms_per_step']}, 'roofline', round(d['roofline']['frac'],4), 'e2e fps', round(d['e2e']['fps'],1))
 PY
-python tools/warp_profile.py $WL > gpurun_out/${TAG}_warps_${WL}.json 2>&1; cat gpurun_out/${TAG}_warps_${WL}.json
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${TAG}_launches_${WL}.csv \
+timeout 120 python tools/warp_profile.py $WL > gpurun_out/${TAG}_warps_${WL}.json 2>&1; cat gpurun_out/${TAG}_warps_${WL}.json
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${TAG}_launches_${WL}.csv \
     python bench.py --workload $WL --steps 4 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 python - <<PY
 import csv

@@ -1,14 +1,9 @@
 #!/bin/bash
-CUDA_LAUNCH_BLOCKING=1 python -m pytest tests/test_gpu_raytrace.py -m gpu -q -x -k "split_pipeline" 2>&1 | tail -5
-compute-sanitizer --tool memcheck python - <<PY 2>&1 | tail -30
-import sys; sys.path.insert(0,'.')
-import renderer_b200 as rb
-from oracle import pyport
-p=pyport.model_path('chessboard.tri')
-s=rb.Scene(p).UpdateBoundingVolumeHierarchy(p+'.bvh')
-g=rb.Renderer(0); g.upload(s)
-cam=rb.Orbit.cameras([40])[40]
-f=rb.make_frame(9,640,360,cam)
-g.set_counters(True)
-a=g.render(f); print(g.counters())
-PY
+# ad-hoc knob sweep on the GPU box: tools/sweep.sh WORKLOAD  (prints warp profiles for a few settings)
+WL=${1:-c2}
+for cfg in "fused 24 2" "fused 16 2" "fused 16 3"; do
+  set -- $cfg
+  echo "== path=$1 refill_below=$2 burst=$3"
+  B200R_RT_PATH=$1 B200R_REFILL_BELOW=$2 B200R_INNER_BURST=$3 timeout 120 python tools/warp_profile.py $WL 2>&1 | tail -1
+  for i in 1 2; do B200R_RT_PATH=$1 B200R_REFILL_BELOW=$2 B200R_INNER_BURST=$3 timeout 200 python bench.py --workload $WL --steps 40 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('ms', round(d['ms_per_step'],4), 'fps', round(d['fps'],1))"; done
+done

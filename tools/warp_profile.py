@@ -22,8 +22,8 @@ L.b200r_get_tile_profile(g._ctx, out.ctypes.data, n.value, C.byref(n))
 w = out.reshape(-1, 4).astype(np.int64)
 w = w[w[:, 0] > 0]
 t0 = w[:, 0].min()
-beg, end, rays = (w[:, 0] - t0) / 1e3, (w[:, 1] - t0) / 1e3, w[:, 2]
-rounds, refills = w[:, 3] & 0xffffffff, w[:, 3] >> 32
+beg, end, rays, shadows = (w[:, 0] - t0) / 1e3, (w[:, 1] - t0) / 1e3, w[:, 2] & 0xfffff, (w[:, 2] >> 20) & 0xfffff
+rounds, refills, rounds_after, drained_us = w[:, 3] & 0xffff, (w[:, 3] >> 16) & 0xfff, (w[:, 3] >> 28) & 0xfff, (w[:, 3] >> 40) / 10.0
 dur = end - beg
 res = {"warps": int(len(w)), "span_us": float(end.max()), "begin_max_us": float(beg.max()),
        "end_pct_us": {p: float(np.percentile(end, p)) for p in (10, 50, 90, 99, 100)},
@@ -31,5 +31,8 @@ res = {"warps": int(len(w)), "span_us": float(end.max()), "begin_max_us": float(
        "rounds_per_warp": {"median": float(np.median(rounds)), "max": int(rounds.max())},
        "refills_per_warp": {"median": float(np.median(refills)), "max": int(refills.max())},
        "us_per_round_median": float(np.median(dur / np.maximum(rounds, 1))),
-       "slowest": [{"end": float(end[i]), "rays": int(rays[i]), "rounds": int(rounds[i]), "refills": int(refills[i])} for i in np.argsort(end)[::-1][:5]]}
+       "drained_us": {p: float(np.percentile(drained_us, p)) for p in (1, 50, 99)},
+       "rounds_after_drain": {"median": float(np.median(rounds_after)), "p90": float(np.percentile(rounds_after, 90)), "max": int(rounds_after.max())},
+       "shadow_rays_per_warp": {"median": float(np.median(shadows)), "max": int(shadows.max()), "sum": int(shadows.sum())},
+       "donated_subtrees": int((w[:, 2] >> 40).sum())}
 print(json.dumps(res))
