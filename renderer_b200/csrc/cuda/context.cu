@@ -190,6 +190,7 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
                 ctx->rt.fuseMode = (getenv("B200R_NO_FUSE") || (pth && !strcmp(pth, "generic"))) ? 0 : ((pth && !strcmp(pth, "jobs")) ? 2 : 1);
             }
             ctx->rt.refillBelow = getenv("B200R_REFILL_BELOW") ? atoi(getenv("B200R_REFILL_BELOW")) : 0;
+            ctx->rt.noRootCull = getenv("B200R_NO_ROOT_RECT") != nullptr;
             ctx->rt.innerBurst = getenv("B200R_INNER_BURST") ? atoi(getenv("B200R_INNER_BURST")) : 0;
             if (getenv("B200R_WARP_PROFILE")) {
                 if (!ctx->rt.warpProf) CU(cudaMalloc((void**)&ctx->rt.warpProf, (size_t)65536 * 32));

@@ -17,6 +17,7 @@ struct RtBuffers {
     bool forceMonolithic = false;
     bool noPrune = false;
     int fuseMode = 1;                          // simple config (1 light, no reflections/AO): 0 generic shade kernel, 1 fused lanes, 2 shadow jobs
+    bool noRootCull = false;                   // B200R_NO_ROOT_RECT: K0 builds every pixel's ray (no screen rectangle)
     unsigned* sdon = nullptr;                  // fused path: merge words of shadow rays split over lanes (all zero between frames)
     void* srays = nullptr; unsigned* sword = nullptr; void* queue2 = nullptr;   // shadow-job pipeline: ray records (48 B), merge words, jobs
     int refillBelow = 0, innerBurst = 0;      // tuning overrides (B200R_REFILL_BELOW / B200R_INNER_BURST), 0 = built-in

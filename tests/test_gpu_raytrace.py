@@ -131,3 +131,21 @@ def test_fused_shadow_continuation_equals_split_pipeline(rb, pyport, load_scene,
     monkeypatch.delenv("B200R_RT_PATH")
     assert np.array_equal(jobs, split) and np.array_equal(fused, split)
     assert_parity(jobs, pyport.render(s, f), f"{model} flags={flags} shadow-job pipeline")
+
+
+@pytest.mark.parametrize("model", ["chessboard.tri", "dragon_vis.ply", "trainColor.tri"])
+def test_root_box_screen_rectangle_culls_nothing_visible(rb, load_scene, gpu, monkeypatch, model):
+    """K0 skips ray construction for pixels outside a conservative screen rectangle of the root box; the frame must be
+    identical to the one where every pixel's ray takes the root test (several orbit positions, two aspect ratios)."""
+    import numpy as np
+    s = load_scene(model)
+    gpu.upload(s)
+    cams = rb.Orbit.cameras([0, 17, 40, 77])
+    for k, cam in cams.items():
+        for (w, h) in ((640, 360), (320, 480)):
+            f = rb.make_frame(rb.MODE_RAYTRACE, w, h, cam, flags=1 | 4)
+            culled = gpu.render(f)
+            monkeypatch.setenv("B200R_NO_ROOT_RECT", "1")
+            full = gpu.render(f)
+            monkeypatch.delenv("B200R_NO_ROOT_RECT")
+            assert np.array_equal(culled, full), f"{model} frame {k} {w}x{h}"

@@ -1,7 +1,7 @@
 #!/bin/bash
 # ad-hoc knob sweep on the GPU box: tools/sweep.sh WORKLOAD  (prints warp profiles for a few settings)
 WL=${1:-c2}
-for cfg in "fused 24 2" "fused 16 2" "fused 16 3"; do
+for cfg in "fused 16 2"; do
   set -- $cfg
   echo "== path=$1 refill_below=$2 burst=$3"
   B200R_RT_PATH=$1 B200R_REFILL_BELOW=$2 B200R_INNER_BURST=$3 timeout 120 python tools/warp_profile.py $WL 2>&1 | tail -1
