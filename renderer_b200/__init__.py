@@ -18,7 +18,7 @@ from ._abi import (F_AO, F_DEFAULT, F_MLAA, F_PHONG_NORMAL, F_REFLECTIONS, F_SHA
                    MODE_RAYTRACE_AA, Counters, Frame)
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libb200render.so")
+LIB_PATH = os.environ.get("B200R_LIB") or os.path.join(_PKG, "libb200render.so")   # (B200R_LIB: developer builds)
 _lib = None
 
 
@@ -263,6 +263,17 @@ class Renderer:
             out = np.empty((rows, frame.width), dtype=np.uint32)
         _check(lib().b200r_render(self._ctx, C.byref(frame), out.ctypes.data), self._ctx)
         return out
+
+    def render_async(self, frame, out):
+        """b200r_render_async: enqueue the frame; `out` (rows x width uint32, ideally page-locked) is complete after
+        wait() or after the second following render_async()."""
+        self._pending = getattr(self, "_pending", [])[-1:] + [out]          # keep the two in-flight buffers alive
+        _check(lib().b200r_render_async(self._ctx, C.byref(frame), out.ctypes.data), self._ctx)
+        return out
+
+    def wait(self):
+        _check(lib().b200r_wait(self._ctx), self._ctx)
+        self._pending = []
 
     def render_device(self, frame, dev_ptr, stream=None):
         _check(lib().b200r_render_device(self._ctx, C.byref(frame), C.c_void_p(dev_ptr),

@@ -66,6 +66,8 @@ SYMBOLS = {
     "b200r_render_shadowmap": (C.c_int, [C.c_void_p, C.c_int, P(C.c_float), P(C.c_float)]),
     "b200r_download_shadowmap": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "b200r_render": (C.c_int, [C.c_void_p, P(Frame), C.c_void_p]),
+    "b200r_render_async": (C.c_int, [C.c_void_p, P(Frame), C.c_void_p]),
+    "b200r_wait": (C.c_int, [C.c_void_p]),
     "b200r_render_device": (C.c_int, [C.c_void_p, P(Frame), C.c_void_p, C.c_void_p]),
     "b200r_mlaa_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "b200r_deinterleave_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,

@@ -39,6 +39,16 @@ struct b200r_ctx {
     // frame resources
     uint32_t* d_frame = nullptr; size_t frame_words = 0;
     uint32_t* h_pinned = nullptr; size_t pinned_words = 0;
+    // b200r_render_async: two frames in flight - frame i's device->host copy runs on copyStream while frame i+1 renders
+    struct AsyncSlot {
+        uint32_t* d = nullptr; size_t words = 0;              // device frame
+        uint32_t* staging = nullptr; size_t staging_words = 0; // pinned staging, used when the caller's buffer is pageable
+        uint32_t* user = nullptr; size_t user_words = 0;       // where the frame finally goes
+        cudaEvent_t rendered = nullptr, copied = nullptr;
+        bool inflight = false, staged = false;
+    } slot[2];
+    cudaStream_t copyStream = nullptr;
+    unsigned asyncIdx = 0;
     unsigned* d_tileCounter = nullptr;
     DeviceCounters* d_ctr = nullptr;
     RasterBuffers rb{};
@@ -337,6 +347,14 @@ void b200r_destroy(b200r_ctx* ctx)
     cudaFree(ctx->d_mlaaScratch); cudaFree(ctx->d_tileProf); cudaFree(ctx->rb.spans); cudaFree(ctx->rb.spanCount); cudaFree(ctx->rb.zkeys); cudaFree(ctx->d_shadowKeys);
     if (ctx->h_spanCount) cudaFreeHost(ctx->h_spanCount);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (auto& S : ctx->slot) {
+        if (S.inflight) cudaEventSynchronize(S.copied);
+        cudaFree(S.d);
+        if (S.staging) cudaFreeHost(S.staging);
+        if (S.rendered) cudaEventDestroy(S.rendered);
+        if (S.copied) cudaEventDestroy(S.copied);
+    }
+    if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -532,6 +550,24 @@ int b200r_render_device(b200r_ctx* ctx, const b200r_frame* f, void* dev_xrgb, vo
     return B200R_OK;
 }
 
+namespace {
+bool host_pointer_is_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int retire_slot(b200r_ctx* ctx, b200r_ctx::AsyncSlot& S)
+{
+    if (!S.inflight) return B200R_OK;
+    CU(cudaEventSynchronize(S.copied));
+    if (S.staged) memcpy(S.user, S.staging, S.user_words * 4);
+    S.inflight = false;
+    return B200R_OK;
+}
+}  // namespace
+
 int b200r_render(b200r_ctx* ctx, const b200r_frame* f, uint32_t* host_xrgb)
 {
     if (!ctx) return fail(nullptr, B200R_EINVAL, "NULL ctx");
@@ -543,7 +579,10 @@ int b200r_render(b200r_ctx* ctx, const b200r_frame* f, uint32_t* host_xrgb)
     const size_t words = (size_t)fp.W * fp.n_rows;
     rc = ensure_frame(ctx, words);
     if (rc) return rc;
-    if (ctx->pinned_words < words) {
+    rc = b200r_wait(ctx);                               // frames still in flight from b200r_render_async
+    if (rc) return rc;
+    const bool direct = host_pointer_is_pinned(host_xrgb);      // page-locked caller memory: DMA straight into it
+    if (!direct && ctx->pinned_words < words) {
         if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
         ctx->h_pinned = nullptr; ctx->pinned_words = 0;
         CU(cudaMallocHost((void**)&ctx->h_pinned, words * 4));
@@ -551,11 +590,65 @@ int b200r_render(b200r_ctx* ctx, const b200r_frame* f, uint32_t* host_xrgb)
     }
     rc = render_common(ctx, f, ctx->d_frame, ctx->stream, fp);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(ctx->h_pinned, ctx->d_frame, words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(direct ? host_xrgb : ctx->h_pinned, ctx->d_frame, words * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaEventElapsedTime(&ctx->last_total_ms, ctx->ev0, ctx->ev1));
     ctx->last_dominant_ms = ctx->last_total_ms;
-    memcpy(host_xrgb, ctx->h_pinned, words * 4);
+    if (!direct) memcpy(host_xrgb, ctx->h_pinned, words * 4);
+    return B200R_OK;
+}
+
+
+int b200r_render_async(b200r_ctx* ctx, const b200r_frame* f, uint32_t* host_xrgb)
+{
+    if (!ctx) return fail(nullptr, B200R_EINVAL, "NULL ctx");
+    if (!host_xrgb) return fail(ctx, B200R_EINVAL, "NULL host frame pointer");
+    CU(cudaSetDevice(ctx->device));
+    FrameParams fp;
+    int rc = make_frame_params(ctx, f, fp);
+    if (rc) return rc;
+    const size_t words = (size_t)fp.W * fp.n_rows;
+    if (!ctx->copyStream) {
+        CU(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+        for (auto& S : ctx->slot) {
+            CU(cudaEventCreateWithFlags(&S.rendered, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&S.copied, cudaEventDisableTiming));
+        }
+    }
+    b200r_ctx::AsyncSlot& S = ctx->slot[ctx->asyncIdx & 1u];
+    rc = retire_slot(ctx, S);                    // the frame submitted two calls ago: its copy must be out of S.d
+    if (rc) return rc;
+    if (S.words < words) {
+        cudaFree(S.d); S.d = nullptr; S.words = 0;
+        CU(cudaMalloc((void**)&S.d, words * 4));
+        S.words = words;
+    }
+    S.staged = !host_pointer_is_pinned(host_xrgb);
+    if (S.staged && S.staging_words < words) {
+        if (S.staging) cudaFreeHost(S.staging);
+        S.staging = nullptr; S.staging_words = 0;
+        CU(cudaMallocHost((void**)&S.staging, words * 4));
+        S.staging_words = words;
+    }
+    rc = render_common(ctx, f, S.d, ctx->stream, fp);
+    if (rc) return rc;
+    CU(cudaEventRecord(S.rendered, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->copyStream, S.rendered, 0));
+    CU(cudaMemcpyAsync(S.staged ? S.staging : host_xrgb, S.d, words * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
+    CU(cudaEventRecord(S.copied, ctx->copyStream));
+    S.user = host_xrgb; S.user_words = words; S.inflight = true;
+    ctx->asyncIdx++;
+    return B200R_OK;
+}
+
+int b200r_wait(b200r_ctx* ctx)
+{
+    if (!ctx) return fail(nullptr, B200R_EINVAL, "NULL ctx");
+    CU(cudaSetDevice(ctx->device));
+    for (unsigned k = 0; k < 2; k++) {           // older submission first
+        int rc = retire_slot(ctx, ctx->slot[(ctx->asyncIdx + k) & 1u]);
+        if (rc) return rc;
+    }
     return B200R_OK;
 }
 

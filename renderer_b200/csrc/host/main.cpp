@@ -128,7 +128,9 @@ int main(int argc, char* argv[])
         }
     }
 
-    std::vector<uint32_t> fb((size_t)W * H);
+    // Frames of the orbit do not depend on each other, so the loop is pipelined: b200r_render_async returns when frame i is
+    // enqueued, its copy-out overlaps frame i+1 (two host frames alternate). Frames that are dumped use the blocking call.
+    std::vector<uint32_t> fb[2] = {std::vector<uint32_t>((size_t)W * H), std::vector<uint32_t>((size_t)W * H)};
     b200r_orbit orbit; b200r_orbit_init(&orbit);
     unsigned framesDrawn = 0;
     double msSpentDrawing = 0, lastReport = now_ms();
@@ -139,14 +141,17 @@ int main(int argc, char* argv[])
         b200r_frame f;
         b200r_frame_defaults(&f, mode, W, H, eye, mv, nLights);
         f.flags = flags; if (ao) f.ao_samples = ao; f.frame_index = framesDrawn;
+        const bool dump = !dumpPrefix.empty() && (dumpFrames.empty() || dumpFrames.count(framesDrawn));
+        std::vector<uint32_t>& out = fb[framesDrawn & 1u];
         const double t0 = now_ms();
-        if (b200r_render(ctx, &f, fb.data())) { fprintf(stderr, "%s\n", b200r_last_error(ctx)); return 1; }
+        const int rc = dump ? b200r_render(ctx, &f, out.data()) : b200r_render_async(ctx, &f, out.data());
+        if (rc) { fprintf(stderr, "%s\n", b200r_last_error(ctx)); return 1; }
         msSpentDrawing += now_ms() - t0;
-        if (!dumpPrefix.empty() && (dumpFrames.empty() || dumpFrames.count(framesDrawn))) {
+        if (dump) {
             const std::string name = dumpPrefix + "_" + std::to_string(framesDrawn) + ".xrgb";
             FILE* fp = fopen(name.c_str(), "wb");
             if (!fp) { perror(name.c_str()); return 2; }
-            fwrite(fb.data(), 4, fb.size(), fp);
+            fwrite(out.data(), 4, out.size(), fp);
             fclose(fp);
         }
         framesDrawn++;
@@ -154,6 +159,11 @@ int main(int argc, char* argv[])
             lastReport = now_ms();
             if (msSpentDrawing > 0) printf("FPS: %g\n", framesDrawn / (msSpentDrawing / 1000.0));
         }
+    }
+    {
+        const double t0 = now_ms();
+        if (b200r_wait(ctx)) { fprintf(stderr, "%s\n", b200r_last_error(ctx)); return 1; }
+        msSpentDrawing += now_ms() - t0;
     }
     if (msSpentDrawing > 0)
         printf("Rendering %u frames in %g seconds. (%g fps)\n", framesDrawn, msSpentDrawing / 1000.0,

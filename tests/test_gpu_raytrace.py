@@ -149,3 +149,30 @@ def test_root_box_screen_rectangle_culls_nothing_visible(rb, load_scene, gpu, mo
             full = gpu.render(f)
             monkeypatch.delenv("B200R_NO_ROOT_RECT")
             assert np.array_equal(culled, full), f"{model} frame {k} {w}x{h}"
+
+
+def test_pipelined_host_render_equals_blocking_call(rb, load_scene, gpu):
+    """b200r_render_async/b200r_wait (two frames in flight, copy-out overlapped) delivers the same frames as b200r_render,
+    into page-locked and into pageable caller memory."""
+    import numpy as np
+    import torch
+    s = load_scene("chessboard.tri")
+    gpu.upload(s)
+    cams = rb.Orbit.cameras(range(6))
+    frames = [rb.make_frame(rb.MODE_RAYTRACE, 640, 360, cams[k], flags=1 | 4, frame_index=k) for k in range(6)]
+    want = [gpu.render(f).copy() for f in frames]
+    pinned = [torch.zeros((360, 640), dtype=torch.int32).pin_memory() for _ in range(6)]
+    outs = [p.numpy().view(np.uint32) for p in pinned]
+    for f, o in zip(frames, outs):
+        gpu.render_async(f, o)
+    gpu.wait()
+    for k in range(6):
+        assert np.array_equal(outs[k], want[k]), f"pinned frame {k}"
+    pageable = [np.zeros((360, 640), dtype=np.uint32) for _ in range(6)]
+    for f, o in zip(frames, pageable):
+        gpu.render_async(f, o)
+    # a blocking call drains the pipeline first
+    again = gpu.render(frames[0])
+    assert np.array_equal(again, want[0])
+    for k in range(6):
+        assert np.array_equal(pageable[k], want[k]), f"pageable frame {k}"
