@@ -51,13 +51,47 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + clock-event (throttle) reasons sampled DURING the timed region (B200_PROFILING.md clocks line).
+    The timed region is short (tens of ms), so NVML is polled from a thread every ~1 ms; `nvidia-smi -lms` (100 ms
+    granularity, ~1 s start-up) is only the fallback when NVML is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.p = None
+        self.thread = None
+        self.samples = []           # (sm_mhz, reasons bitmask)
+        self.max_mhz = None
+        self._stop = False
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except Exception:
+                    phys = index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.nv = nv
+
+            def poll():
+                while not self._stop:
+                    try:
+                        self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                             int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
+                    except Exception:
+                        pass
+                    time.sleep(0.001)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
                                        "--format=csv,noheader,nounits", "-lms", "100"],
@@ -66,6 +100,18 @@ class ClockSampler:
             self.p = None
 
     def stop(self):
+        if self.thread:
+            self._stop = True
+            self.thread.join(timeout=2)
+            nv = self.nv
+            names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                     ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                     ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+            sm = sorted(s_[0] for s_ in self.samples)
+            reasons = sorted({n for _, bits in self.samples for n, b in names if bits & b})
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "NVML polled every ~1 ms during the timed region"}
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.12)
@@ -89,7 +135,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # --------------------------------------------------------------------------- CPU reference arm
@@ -270,7 +316,7 @@ def run_b200_arm(args, wl):
         (gpu.wait() before the clock stops); pipelined=False times the blocking b200r_render instead."""
         if P == 1:
             if pipelined:
-                gpu.render_async(frame_for(step), host_ring[step & 1])
+                gpu.render_async(frame_for(step), host_ring[step % 3])
             else:
                 gpu.render(frame_for(step), out=host_np)
         else:
@@ -281,7 +327,8 @@ def run_b200_arm(args, wl):
 
     host_np = host.numpy().view(np.uint32)
     host2 = torch.zeros((H, W), dtype=torch.int32).pin_memory()
-    host_ring = [host_np, host2.numpy().view(np.uint32)]
+    host3 = torch.zeros((H, W), dtype=torch.int32).pin_memory()
+    host_ring = [host_np, host2.numpy().view(np.uint32), host3.numpy().view(np.uint32)]
 
     def barrier():
         if P > 1:
@@ -399,8 +446,10 @@ def run_b200_arm(args, wl):
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "fps": K / e2e_s,
                     "h2d_bytes_per_step": C.sizeof(rb.Frame), "d2h_bytes_per_step": W * H * 4,
                     "fps_blocking_call": K / e2e_sync_s,
-                    "note": ("b200r_render_async + b200r_wait with page-locked host frames: frame state in, XRGB frame out, per step, "
-                             "copy-out of frame i overlapped with frame i+1; fps_blocking_call = one blocking b200r_render per step")
+                    "note": ("b200r_render_async + b200r_wait with page-locked host frames: frame state in, XRGB frame out, per step; "
+                             "up to 3 frames in flight (frame i copying out while frames i+1, i+2 render on two streams, the head of "
+                             "one filling the SMs the tail of the other leaves idle); every frame is complete in host memory before "
+                             "the clock stops; fps_blocking_call = one blocking b200r_render per step")
                             if P == 1 else "frame rendered row-cyclically on all ranks, gathered, copied to rank 0's host memory, per step"},
             "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall,
         }

@@ -147,9 +147,11 @@ int  b200r_download_shadowmap(b200r_ctx* ctx, int light, float* map1024x1024);
 int  b200r_render(b200r_ctx* ctx, const b200r_frame* f, uint32_t* host_xrgb);
 
 /* The same call, pipelined - for loops like main()'s benchmark loop (src/renderer.cc:491-606), where frame i+1 does
- * not depend on frame i: the call returns once the frame is ENQUEUED; its device->host copy then overlaps the next
- * frame's kernels (two frames in flight). host_xrgb must stay valid, and is only complete, after b200r_wait() - or
- * after the second following b200r_render_async(), which reuses the slot. Page-locked caller memory is written by
+ * not depend on frame i: the call returns once the frame is ENQUEUED. Up to three frames are in flight: one being
+ * copied to the host while the next two render; ray-traced frames alternate between two streams and scratch sets, so
+ * the head of frame i+1 runs on the SMs that the tail of frame i (its last few long rays) leaves idle.
+ * host_xrgb must stay valid, and is only complete, after b200r_wait() - or after the third following
+ * b200r_render_async(), which reuses the slot. Page-locked caller memory is written by
  * DMA directly; pageable memory goes through an internal pinned staging buffer (copied out in b200r_wait / slot reuse).
  * b200r_render() and b200r_destroy() drain the pipeline first. */
 int  b200r_render_async(b200r_ctx* ctx, const b200r_frame* f, uint32_t* host_xrgb);

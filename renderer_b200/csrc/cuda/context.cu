@@ -46,8 +46,14 @@ struct b200r_ctx {
         uint32_t* user = nullptr; size_t user_words = 0;       // where the frame finally goes
         cudaEvent_t rendered = nullptr, copied = nullptr;
         bool inflight = false, staged = false;
-    } slot[2];
+    } slot[3];
+    static constexpr unsigned NSLOT = 3;       // frames in flight: one being copied out, two rendering (overlapped, see stream2)
     cudaStream_t copyStream = nullptr;
+    // ... and frame i+1's ray-tracing kernels run on a second stream with a second set of scratch buffers, so they fill the
+    // SMs that the tail of frame i's persistent kernel leaves idle (its last few long rays)
+    cudaStream_t stream2 = nullptr;
+    RtBuffers rt2{};
+    unsigned* d_tileCounter2 = nullptr;
     unsigned asyncIdx = 0;
     unsigned* d_tileCounter = nullptr;
     DeviceCounters* d_ctr = nullptr;
@@ -150,7 +156,7 @@ int mlaa_on(b200r_ctx* ctx, uint32_t* d_frame, uint32_t width, uint32_t height, 
     return B200R_OK;
 }
 
-int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStream_t stream, FrameParams& fp)
+int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStream_t stream, FrameParams& fp, int scratchSet = 0)
 {
     int rc = make_frame_params(ctx, f, fp);
     if (rc) return rc;
@@ -175,39 +181,46 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
                 prof = ctx->d_tileProf; ctx->lastTiles = nTiles;
             }
             const size_t px32 = (size_t)nTiles * 32;
-            if (ctx->rt.pixels < px32) {
-                cudaFree(ctx->rt.queue); cudaFree(ctx->rt.hits); cudaFree(ctx->rt.keys); cudaFree(ctx->rt.pend);
-                ctx->rt.queue = nullptr; ctx->rt.hits = nullptr; ctx->rt.keys = nullptr; ctx->rt.pend = nullptr; ctx->rt.pixels = 0;
-                CU(cudaMalloc((void**)&ctx->rt.queue, px32 * 8 * 8));        // <= 8 jobs of 8 bytes per pixel
-                CU(cudaMalloc((void**)&ctx->rt.hits, px32 * 32));
-                CU(cudaMalloc((void**)&ctx->rt.keys, px32 * 8));
-                cudaFree(ctx->rt.srays); cudaFree(ctx->rt.sword); cudaFree(ctx->rt.queue2);
-                ctx->rt.srays = nullptr; ctx->rt.sword = nullptr; ctx->rt.queue2 = nullptr;
-                CU(cudaMalloc((void**)&ctx->rt.srays, px32 * 48));
-                CU(cudaMalloc((void**)&ctx->rt.sword, px32 * 4));
-                cudaFree(ctx->rt.sdon); ctx->rt.sdon = nullptr;
-                CU(cudaMalloc((void**)&ctx->rt.sdon, px32 * 4));
-                CU(cudaMemsetAsync(ctx->rt.sdon, 0, px32 * 4, stream));
-                CU(cudaMalloc((void**)&ctx->rt.queue2, px32 * 8 * 8));
-                CU(cudaMalloc((void**)&ctx->rt.pend, px32 * 4));
-                ctx->rt.pixels = px32;
+            RtBuffers& rt = scratchSet ? ctx->rt2 : ctx->rt;
+            if (rt.pixels < px32) {
+                cudaFree(rt.queue); cudaFree(rt.hits); cudaFree(rt.keys); cudaFree(rt.pend);
+                rt.queue = nullptr; rt.hits = nullptr; rt.keys = nullptr; rt.pend = nullptr; rt.pixels = 0;
+                CU(cudaMalloc((void**)&rt.queue, px32 * 8 * 8));        // <= 8 jobs of 8 bytes per pixel
+                CU(cudaMalloc((void**)&rt.hits, px32 * 32));
+                CU(cudaMalloc((void**)&rt.keys, px32 * 8));
+                cudaFree(rt.srays); cudaFree(rt.sword); cudaFree(rt.queue2);
+                rt.srays = nullptr; rt.sword = nullptr; rt.queue2 = nullptr;
+                CU(cudaMalloc((void**)&rt.srays, px32 * 48));
+                CU(cudaMalloc((void**)&rt.sword, px32 * 4));
+                cudaFree(rt.sdon); rt.sdon = nullptr;
+                CU(cudaMalloc((void**)&rt.sdon, px32 * 4));
+                CU(cudaMemsetAsync(rt.sdon, 0, px32 * 4, stream));
+                CU(cudaMalloc((void**)&rt.queue2, px32 * 8 * 8));
+                CU(cudaMalloc((void**)&rt.pend, px32 * 4));
+                rt.pixels = px32;
             }
-            ctx->rt.counters = ctx->d_tileCounter;
-            ctx->rt.forceMonolithic = getenv("B200R_MONOLITHIC_RT") != nullptr;
-            ctx->rt.noPrune = getenv("B200R_NO_PRUNE") != nullptr;
+            rt.counters = scratchSet ? ctx->d_tileCounter2 : ctx->d_tileCounter;
+            rt.forceMonolithic = getenv("B200R_MONOLITHIC_RT") != nullptr;
+            rt.noPrune = getenv("B200R_NO_PRUNE") != nullptr;
             {
                 const char* pth = getenv("B200R_RT_PATH");       // generic | fused (default) | jobs
-                ctx->rt.fuseMode = (getenv("B200R_NO_FUSE") || (pth && !strcmp(pth, "generic"))) ? 0 : ((pth && !strcmp(pth, "jobs")) ? 2 : 1);
+                rt.fuseMode = (getenv("B200R_NO_FUSE") || (pth && !strcmp(pth, "generic"))) ? 0 : ((pth && !strcmp(pth, "jobs")) ? 2 : 1);
             }
-            ctx->rt.refillBelow = getenv("B200R_REFILL_BELOW") ? atoi(getenv("B200R_REFILL_BELOW")) : 0;
-            ctx->rt.noRootCull = getenv("B200R_NO_ROOT_RECT") != nullptr;
-            ctx->rt.innerBurst = getenv("B200R_INNER_BURST") ? atoi(getenv("B200R_INNER_BURST")) : 0;
+            rt.refillBelow = getenv("B200R_REFILL_BELOW") ? atoi(getenv("B200R_REFILL_BELOW")) : 0;
+            rt.noRootCull = getenv("B200R_NO_ROOT_RECT") != nullptr;
+            rt.sched = (getenv("B200R_RT_SCHED") && !strcmp(getenv("B200R_RT_SCHED"), "wave")) ? 1 : 0;
+            rt.lateWeight = getenv("B200R_LATE_WEIGHT") ? atoi(getenv("B200R_LATE_WEIGHT")) : 0;
+            rt.prefetchCur = getenv("B200R_NO_PREFETCH_CUR") ? 0 : 1;
+            rt.longT = getenv("B200R_LONG_T") ? atoi(getenv("B200R_LONG_T")) : 0;
+            rt.splitDepth = getenv("B200R_SPLIT_DEPTH") ? atoi(getenv("B200R_SPLIT_DEPTH")) : -1;
+            rt.blocksPerSM = getenv("B200R_BLOCKS_PER_SM") ? atoi(getenv("B200R_BLOCKS_PER_SM")) : 0;
+            rt.innerBurst = getenv("B200R_INNER_BURST") ? atoi(getenv("B200R_INNER_BURST")) : 0;
             if (getenv("B200R_WARP_PROFILE")) {
-                if (!ctx->rt.warpProf) CU(cudaMalloc((void**)&ctx->rt.warpProf, (size_t)65536 * 32));
+                if (!rt.warpProf) CU(cudaMalloc((void**)&rt.warpProf, (size_t)65536 * 32));
                 prof = nullptr;
-            } else if (ctx->rt.warpProf) { cudaFree(ctx->rt.warpProf); ctx->rt.warpProf = nullptr; }
+            } else if (rt.warpProf) { cudaFree(rt.warpProf); rt.warpProf = nullptr; }
             int launches = 0;
-            CU(launch_raytrace(ctx->sc, fp, d_out, ctx->rt, ctx->d_ctr, ctx->counting, prof, ctx->numSMs, stream, launches));
+            CU(launch_raytrace(ctx->sc, fp, d_out, rt, ctx->d_ctr, ctx->counting, prof, ctx->numSMs, stream, launches));
             ctx->last_launches += (uint32_t)launches;
         }
         break;
@@ -344,6 +357,10 @@ void b200r_destroy(b200r_ctx* ctx)
     cudaFree(ctx->wb.counts); cudaFree(ctx->wb.offsets); cudaFree(ctx->wb.blockSums); cudaFree(ctx->wb.total); cudaFree(ctx->wb.frags);
     cudaFree(ctx->rt.queue); cudaFree(ctx->rt.hits); cudaFree(ctx->rt.keys); cudaFree(ctx->rt.pend);
     cudaFree(ctx->rt.srays); cudaFree(ctx->rt.sword); cudaFree(ctx->rt.queue2); cudaFree(ctx->rt.warpProf); cudaFree(ctx->rt.sdon);
+    cudaFree(ctx->rt2.queue); cudaFree(ctx->rt2.hits); cudaFree(ctx->rt2.keys); cudaFree(ctx->rt2.pend);
+    cudaFree(ctx->rt2.srays); cudaFree(ctx->rt2.sword); cudaFree(ctx->rt2.queue2); cudaFree(ctx->rt2.warpProf); cudaFree(ctx->rt2.sdon);
+    cudaFree(ctx->d_tileCounter2);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     cudaFree(ctx->d_mlaaScratch); cudaFree(ctx->d_tileProf); cudaFree(ctx->rb.spans); cudaFree(ctx->rb.spanCount); cudaFree(ctx->rb.zkeys); cudaFree(ctx->d_shadowKeys);
     if (ctx->h_spanCount) cudaFreeHost(ctx->h_spanCount);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -540,7 +557,9 @@ int b200r_render_device(b200r_ctx* ctx, const b200r_frame* f, void* dev_xrgb, vo
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     FrameParams fp;
-    int rc = render_common(ctx, f, (uint32_t*)dev_xrgb, s, fp);
+    int rc = b200r_wait(ctx);                   // frames of b200r_render_async still in flight use the same scratch buffers
+    if (rc) return rc;
+    rc = render_common(ctx, f, (uint32_t*)dev_xrgb, s, fp);
     if (rc) return rc;
     if (!cuda_stream) {
         CU(cudaStreamSynchronize(s));
@@ -615,8 +634,8 @@ int b200r_render_async(b200r_ctx* ctx, const b200r_frame* f, uint32_t* host_xrgb
             CU(cudaEventCreateWithFlags(&S.copied, cudaEventDisableTiming));
         }
     }
-    b200r_ctx::AsyncSlot& S = ctx->slot[ctx->asyncIdx & 1u];
-    rc = retire_slot(ctx, S);                    // the frame submitted two calls ago: its copy must be out of S.d
+    b200r_ctx::AsyncSlot& S = ctx->slot[ctx->asyncIdx % b200r_ctx::NSLOT];
+    rc = retire_slot(ctx, S);                    // the frame submitted NSLOT calls ago: its copy must be out of S.d
     if (rc) return rc;
     if (S.words < words) {
         cudaFree(S.d); S.d = nullptr; S.words = 0;
@@ -630,9 +649,20 @@ int b200r_render_async(b200r_ctx* ctx, const b200r_frame* f, uint32_t* host_xrgb
         CU(cudaMallocHost((void**)&S.staging, words * 4));
         S.staging_words = words;
     }
-    rc = render_common(ctx, f, S.d, ctx->stream, fp);
+    // Ray-traced frames alternate between two streams / scratch sets: frame i+1 starts while the last long rays of frame i
+    // are still being walked (the persistent kernel's CTAs retire one by one) and takes over the SMs they free.
+    // Everything else (and any profiling / counting run) stays on the one stream and is therefore serialised.
+    const bool overlap = (fp.mode == B200R_MODE_RAYTRACE || fp.mode == B200R_MODE_RAYTRACE_AA) && !ctx->counting && !ctx->tileProfile &&
+                         !getenv("B200R_WARP_PROFILE") && !getenv("B200R_NO_FRAME_OVERLAP") && !(f->flags & B200R_F_MLAA);
+    const int set = overlap ? (int)(ctx->asyncIdx & 1u) : 0;
+    if (set && !ctx->stream2) {
+        CU(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+        CU(cudaMalloc((void**)&ctx->d_tileCounter2, 64));
+    }
+    cudaStream_t rs = set ? ctx->stream2 : ctx->stream;
+    rc = render_common(ctx, f, S.d, rs, fp, set);
     if (rc) return rc;
-    CU(cudaEventRecord(S.rendered, ctx->stream));
+    CU(cudaEventRecord(S.rendered, rs));
     CU(cudaStreamWaitEvent(ctx->copyStream, S.rendered, 0));
     CU(cudaMemcpyAsync(S.staged ? S.staging : host_xrgb, S.d, words * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
     CU(cudaEventRecord(S.copied, ctx->copyStream));
@@ -645,8 +675,8 @@ int b200r_wait(b200r_ctx* ctx)
 {
     if (!ctx) return fail(nullptr, B200R_EINVAL, "NULL ctx");
     CU(cudaSetDevice(ctx->device));
-    for (unsigned k = 0; k < 2; k++) {           // older submission first
-        int rc = retire_slot(ctx, ctx->slot[(ctx->asyncIdx + k) & 1u]);
+    for (unsigned k = 0; k < b200r_ctx::NSLOT; k++) {           // oldest submission first
+        int rc = retire_slot(ctx, ctx->slot[(ctx->asyncIdx + k) % b200r_ctx::NSLOT]);
         if (rc) return rc;
     }
     return B200R_OK;
@@ -704,7 +734,7 @@ int b200r_get_tile_profile(b200r_ctx* ctx, uint64_t* start_end_ns, uint32_t max_
 {
     if (!ctx || !n_tiles) return fail(ctx, B200R_EINVAL, "NULL argument");
     if (ctx->rt.warpProf) {      // B200R_WARP_PROFILE: per-warp records of rt_primary_kernel (2 "tiles" per warp)
-        *n_tiles = ctx->rt.lastPrimaryWarps * 2;
+        *n_tiles = getenv("B200R_JOB_PROFILE") ? 131072u : ctx->rt.lastPrimaryWarps * 2;     // whole buffer incl. job statistics
         if (!start_end_ns) return B200R_OK;
         CU(cudaSetDevice(ctx->device));
         const uint32_t n = *n_tiles < max_tiles ? *n_tiles : max_tiles;

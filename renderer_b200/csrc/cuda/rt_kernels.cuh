@@ -21,6 +21,9 @@ struct RtBuffers {
     unsigned* sdon = nullptr;                  // fused path: merge words of shadow rays split over lanes (all zero between frames)
     void* srays = nullptr; unsigned* sword = nullptr; void* queue2 = nullptr;   // shadow-job pipeline: ray records (48 B), merge words, jobs
     int refillBelow = 0, innerBurst = 0;      // tuning overrides (B200R_REFILL_BELOW / B200R_INNER_BURST), 0 = built-in
+    int sched = 0;                             // 0: rt_primary_kernel (rounds, default); 1: rt_wave_kernel (state-voting scheduler, measured slower) - B200R_RT_SCHED=wave
+    int lateWeight = 0, prefetchCur = 1, longT = 0;   // rt_wave_kernel tuning (B200R_LATE_WEIGHT / B200R_NO_PREFETCH_CUR / B200R_LONG_T)
+    int splitDepth = -1, blocksPerSM = 0;       // B200R_SPLIT_DEPTH (0..3, default 2) / B200R_BLOCKS_PER_SM (cap on resident CTAs of the persistent kernel)
     unsigned long long* warpProf = nullptr;   // developer tool (B200R_WARP_PROFILE): 4 x u64 per warp of rt_primary_kernel
     unsigned lastPrimaryWarps = 0;
 };

@@ -129,8 +129,8 @@ int main(int argc, char* argv[])
     }
 
     // Frames of the orbit do not depend on each other, so the loop is pipelined: b200r_render_async returns when frame i is
-    // enqueued, its copy-out overlaps frame i+1 (two host frames alternate). Frames that are dumped use the blocking call.
-    std::vector<uint32_t> fb[2] = {std::vector<uint32_t>((size_t)W * H), std::vector<uint32_t>((size_t)W * H)};
+    // enqueued, its copy-out and its tail overlap the following frames (three host frames rotate). Dumped frames use the blocking call.
+    std::vector<uint32_t> fb[3] = {std::vector<uint32_t>((size_t)W * H), std::vector<uint32_t>((size_t)W * H), std::vector<uint32_t>((size_t)W * H)};
     b200r_orbit orbit; b200r_orbit_init(&orbit);
     unsigned framesDrawn = 0;
     double msSpentDrawing = 0, lastReport = now_ms();
@@ -142,7 +142,7 @@ int main(int argc, char* argv[])
         b200r_frame_defaults(&f, mode, W, H, eye, mv, nLights);
         f.flags = flags; if (ao) f.ao_samples = ao; f.frame_index = framesDrawn;
         const bool dump = !dumpPrefix.empty() && (dumpFrames.empty() || dumpFrames.count(framesDrawn));
-        std::vector<uint32_t>& out = fb[framesDrawn & 1u];
+        std::vector<uint32_t>& out = fb[framesDrawn % 3u];
         const double t0 = now_ms();
         const int rc = dump ? b200r_render(ctx, &f, out.data()) : b200r_render_async(ctx, &f, out.data());
         if (rc) { fprintf(stderr, "%s\n", b200r_last_error(ctx)); return 1; }

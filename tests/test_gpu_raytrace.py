@@ -133,6 +133,32 @@ def test_fused_shadow_continuation_equals_split_pipeline(rb, pyport, load_scene,
     assert_parity(jobs, pyport.render(s, f), f"{model} flags={flags} shadow-job pipeline")
 
 
+@pytest.mark.parametrize("flags", [1 | 4, 1 | 2 | 4, 4])
+@pytest.mark.parametrize("model,size", [("chessboard.tri", (1920, 1080)), ("dragon_vis.ply", (1280, 720)), ("single.ply", (320, 240)),
+                                        ("trainColor.tri", (800, 600))])
+def test_state_voting_scheduler_equals_round_scheduler(rb, pyport, load_scene, gpu, monkeypatch, model, size, flags):
+    """rt_wave_kernel (one phase per warp iteration, chosen by vote; experimental) against rt_primary_kernel (all phases
+    every round; the default): same jobs, same merges - the frames must be identical, fused and generic paths, and equal the
+    oracle."""
+    import numpy as np
+    s = load_scene(model)
+    gpu.upload(s)
+    for k, cam in rb.Orbit.cameras([3, 64]).items():
+        f = rb.make_frame(rb.MODE_RAYTRACE, size[0], size[1], cam, flags=flags)
+        rounds = gpu.render(f)
+        monkeypatch.setenv("B200R_RT_SCHED", "wave")
+        wave = gpu.render(f)
+        assert np.array_equal(wave, rounds), f"{model} frame {k} flags={flags}"
+        for rf in (1, 32):                                  # refill thresholds at both extremes
+            monkeypatch.setenv("B200R_REFILL_BELOW", str(rf))
+            again = gpu.render(f)
+            monkeypatch.delenv("B200R_REFILL_BELOW")
+            assert np.array_equal(wave, again), f"{model} frame {k} flags={flags} refillMin={rf}"
+        monkeypatch.delenv("B200R_RT_SCHED")
+        if k == 3 and size[0] <= 1280:
+            assert_parity(wave, pyport.render(s, f), f"{model} {size} frame {k} flags={flags}")
+
+
 @pytest.mark.parametrize("model", ["chessboard.tri", "dragon_vis.ply", "trainColor.tri"])
 def test_root_box_screen_rectangle_culls_nothing_visible(rb, load_scene, gpu, monkeypatch, model):
     """K0 skips ray construction for pixels outside a conservative screen rectangle of the root box; the frame must be
@@ -176,3 +202,28 @@ def test_pipelined_host_render_equals_blocking_call(rb, load_scene, gpu):
     assert np.array_equal(again, want[0])
     for k in range(6):
         assert np.array_equal(pageable[k], want[k]), f"pageable frame {k}"
+
+
+def test_overlapped_async_frames_equal_blocking_frames(rb, load_scene, gpu):
+    """b200r_render_async alternates ray-traced frames between two streams / scratch sets so that frame i+1 fills the SMs the
+    tail of frame i leaves idle. Frames of different sizes, modes and feature sets submitted back to back must each equal
+    the blocking call's frame."""
+    import numpy as np
+    import torch
+    s = load_scene("chessboard.tri")
+    gpu.upload(s)
+    cams = rb.Orbit.cameras(range(12))
+    specs = [(rb.MODE_RAYTRACE, 1920, 1080, 1 | 4), (rb.MODE_RAYTRACE, 1920, 1080, 1 | 4), (rb.MODE_RAYTRACE, 1280, 720, 1 | 2 | 4),
+             (rb.MODE_PHONG, 800, 600, 0), (rb.MODE_RAYTRACE, 1920, 1080, 1 | 4), (rb.MODE_RAYTRACE_AA, 320, 240, 1 | 2 | 4),
+             (rb.MODE_RAYTRACE, 1920, 1080, 4), (rb.MODE_RAYTRACE, 1920, 1080, 1 | 4), (rb.MODE_RAYTRACE, 640, 360, 1 | 4),
+             (rb.MODE_RAYTRACE, 1920, 1080, 1 | 4), (rb.MODE_RAYTRACE, 1920, 1080, 1 | 4), (rb.MODE_RAYTRACE, 1920, 1080, 1 | 4)]
+    frames = [rb.make_frame(m, w, h, cams[k], flags=fl, frame_index=k) for k, (m, w, h, fl) in enumerate(specs)]
+    want = [gpu.render(f).copy() for f in frames]
+    for rep in range(2):
+        pinned = [torch.zeros((h, w), dtype=torch.int32).pin_memory() for (_, w, h, _) in specs]
+        outs = [p.numpy().view(np.uint32) for p in pinned]
+        for f, o in zip(frames, outs):
+            gpu.render_async(f, o)
+        gpu.wait()
+        for k in range(len(frames)):
+            assert np.array_equal(outs[k], want[k]), f"rep {rep} frame {k} {specs[k]}"
