@@ -273,6 +273,8 @@ def run_b200_arm(args, wl):
     torch.cuda.set_device(local)
     dist = None
     if P > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -290,8 +292,12 @@ def run_b200_arm(args, wl):
         return rb.make_frame(wl["mode"], W, H, cams[step], flags=wl["flags"], ao_samples=wl["ao"] or 32,
                              frame_index=step, row_first=0 if full else rank, row_step=1 if full else P)
 
-    stream = torch.cuda.current_stream()
+    # Everything timed runs on ONE explicit stream: the L2 flush, the events, the renderer's kernels (b200r_render_device enqueues on
+    # the stream it is given; the legacy default stream, handle 0, would mean "library stream + host sync") and NCCL's waits.
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
+    assert sptr != 0
     shard = torch.zeros((rows_per, W), dtype=torch.int32, device="cuda")
     gathered = torch.zeros((P * rows_per, W), dtype=torch.int32, device="cuda") if P > 1 else None
     full = torch.zeros((H, W), dtype=torch.int32, device="cuda")
@@ -359,8 +365,7 @@ def run_b200_arm(args, wl):
         step_device(s)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(K)]
+    ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(4)) for _ in range(K)]
     launches = 0
     t_wall0 = time.perf_counter()
     for i in range(K):
@@ -374,6 +379,7 @@ def run_b200_arm(args, wl):
             launches += gpu.last_launches() + 1
             ev[i][1].record()
             dist.all_gather_into_tensor(gathered, shard)
+            ev[i][3].record()
             gpu.deinterleave_device(gathered.data_ptr(), full.data_ptr(), W, H, P, sptr)
         ev[i][2].record()
     barrier()
@@ -383,7 +389,14 @@ def run_b200_arm(args, wl):
     kern_ms = [e[0].elapsed_time(e[1]) for e in ev]
     total_ms = sum(step_ms)
     kern_total_ms = sum(kern_ms)
+    per_rank = None
     if P > 1:
+        gather_ms = sum(e[1].elapsed_time(e[3]) for e in ev)          # includes waiting for the slowest rank's kernels
+        mine = torch.tensor([total_ms, kern_total_ms, gather_ms], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(P)]
+        dist.all_gather(allr, mine)
+        per_rank = {"step_ms": [float(a[0]) / K for a in allr], "render_kernels_ms": [float(a[1]) / K for a in allr],
+                    "all_gather_incl_wait_ms": [float(a[2]) / K for a in allr]}
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
@@ -453,6 +466,8 @@ def run_b200_arm(args, wl):
                             if P == 1 else "frame rendered row-cyclically on all ranks, gathered, copied to rank 0's host memory, per step"},
             "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall,
         }
+        if per_rank:
+            line["per_rank"] = per_rank
         print(json.dumps(line))
     if P > 1:
         dist.barrier()

@@ -1,3 +1,10 @@
 mkdir -p gpurun_out
-B200R_RT_SCHED=rounds B200R_EAGER_T=6 timeout 900 python -m pytest tests/test_gpu_raytrace.py tests/test_gpu_raster.py -m gpu -q -x -k "raytrace or scheduler or fused or async or pipelined or pruning" > gpurun_out/eager_pytest.log 2>&1; tail -3 gpurun_out/eager_pytest.log
-SKIP_TESTS=1 bash tools/gpu_ab.sh ab6 c2 "B200R_RT_SCHED=rounds B200R_EAGER_T=4" "B200R_RT_SCHED=rounds B200R_EAGER_T=8" "B200R_RT_SCHED=rounds B200R_EAGER_T=16" "B200R_RT_SCHED=rounds B200R_EAGER_T=8 B200R_REFILL_BELOW=12" "B200R_RT_SCHED=rounds B200R_EAGER_T=8 B200R_REFILL_BELOW=20" "B200R_RT_SCHED=rounds B200R_EAGER_T=8 B200R_SPLIT_DEPTH=1" "B200R_RT_SCHED=rounds B200R_EAGER_T=8 B200R_SPLIT_DEPTH=0"
+for i in 1 2; do timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline 2>gpurun_out/n1.err | python -c "
+import json,sys
+d=json.loads([l for l in sys.stdin.read().splitlines() if l.startswith('{')][-1])
+print('N1', {k:round(d[k],4) for k in ('value','fps','ms_per_step')}, round(d['roofline']['kernel_ms'],4), round(d['roofline']['frac'],3), 'e2e', round(d['e2e']['fps'],1), round(d['e2e']['fps_blocking_call'],1), d['clocks'])"; done
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 5 2> gpurun_out/n2_bench.err | python -c "
+import json,sys
+d=json.loads([l for l in sys.stdin.read().splitlines() if l.startswith('{')][-1])
+print('N2', {k:round(d[k],4) for k in ('value','fps','ms_per_step')}, round(d['roofline']['kernel_ms'],4), 'e2e', round(d['e2e']['fps'],1)); print(d.get('per_rank'))"
+tail -3 gpurun_out/n2_bench.err | cut -c1-300
