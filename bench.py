@@ -32,12 +32,21 @@ WORKLOADS = {
                desc="dragon_vis.ply 1920x1080 mode 9 + 16-sample AO + reflections"),
     "c5": dict(model="chessboard.tri", W=3840, H=2160, mode=9, flags=1 | 2 | 4 | 8, ao=16, ref=dict(ao=16),
                desc="chessboard.tri 3840x2160 mode 9 + reflections + 16-sample AO"),
+    # rasteriser (BASELINE config 4): the metric of this line is fps (there are no rays); flags 0x10 = MLAA post filter
+    "c4": dict(model="statue.ply", W=3840, H=2160, mode=6, flags=1 | 2 | 4 | 0x10, ao=0, ref=dict(mlaa=True), raster=True,
+               desc="statue.ply 3840x2160 mode 6: per-pixel Phong scan-conversion rasteriser + Z-buffer + MLAA"),
+    "c4g": dict(model="statue.ply", W=3840, H=2160, mode=5, flags=1 | 2 | 4 | 0x10, ao=0, ref=dict(mlaa=True), raster=True,
+                desc="statue.ply 3840x2160 mode 5: Gouraud scan-conversion rasteriser + Z-buffer + MLAA"),
 }
 
 
-def algorithmic_bytes(c, W, rows):
+def algorithmic_bytes(c, W, rows, raster=False):
     """32 B per node popped (inner test or leaf visit), 68 B per triangle tested (4-B index +
-    64 B of plane/edge data) + 16 B (centre + twoSided) because culling is on for every ray, + 4 B per pixel."""
+    64 B of plane/edge data) + 16 B (centre + twoSided) because culling is on for every ray, + 4 B per pixel.
+    Rasteriser (same section): 3 vertices of 28 B + the 144-B triangle per triangle set up, 8 B per z-test,
+    4 B per z-pass, and the two clears (frame + depth) of 4 B per pixel each."""
+    if raster:
+        return (28 * 3 + 144) * c["tris_setup"] + 8 * c["z_tests"] + 4 * c["z_passes"] + 2 * 4 * W * rows
     return 32 * (c["node_tests"] + c["leaf_visits"]) + (68 + 16) * c["tri_tests"] + 4 * W * rows
 
 
@@ -190,13 +199,14 @@ def cpu_reference(wl, target_seconds=15.0, rays_per_frame=None, runner=None):
     if that binary was not built."""
     from oracle import pyport
     if rays_per_frame is None:
-        rays_per_frame = port_rays_per_frame(wl)
+        rays_per_frame = 0 if wl.get("raster") else port_rays_per_frame(wl)
     r = runner or RefRunner(wl)
     if r.ok:
         if r.fps0 is None:
             r.calibrate()
         n, fps = r.sample(target_seconds)
-        return {"value": rays_per_frame * fps / 1e6, "unit": "Mrays/s", "fps": fps, "cores": r.threads,
+        return {"value": fps if wl.get("raster") else rays_per_frame * fps / 1e6, "unit": "fps" if wl.get("raster") else "Mrays/s",
+                "fps": fps, "cores": r.threads,
                 "host_cpus": os.cpu_count(), "kind": "reference",
                 "sample": f"{n} orbit frames of [{wl['desc']}] by the unmodified reference built with its own flags "
                           f"(-O3 -ffast-math -mrecip -fopenmp, SSE paths); OMP_NUM_THREADS={r.threads} (best of "
@@ -211,8 +221,8 @@ def cpu_reference(wl, target_seconds=15.0, rays_per_frame=None, runner=None):
         f = rb.make_frame(wl["mode"], W, H, cams[n], flags=wl["flags"], ao_samples=wl["ao"] or 32, frame_index=n)
         pyport.render(scene, f); n += 1
     fps = n / (time.time() - t0)
-    return {"value": rays_per_frame * fps / 1e6, "unit": "Mrays/s", "fps": fps, "cores": os.cpu_count(),
-            "host_cpus": os.cpu_count(), "kind": "port",
+    return {"value": fps if wl.get("raster") else rays_per_frame * fps / 1e6, "unit": "fps" if wl.get("raster") else "Mrays/s",
+            "fps": fps, "cores": os.cpu_count(), "host_cpus": os.cpu_count(), "kind": "port",
             "sample": f"{n} orbit frames of [{wl['desc']}] by oracle/port (C++ restatement, OpenMP over rows)"}
 
 
@@ -233,7 +243,8 @@ def run_reference_arm(args, wl):
     if rank != 0:
         return
     t0 = time.time()
-    rays = port_rays_per_frame(wl)
+    raster = bool(wl.get("raster"))
+    rays = 0 if raster else port_rays_per_frame(wl)
     # each "step" is a bounded sample: the reference renders a batch of orbit frames; K+W batches in total
     per_step = max(1.5, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
     vals = []
@@ -243,14 +254,15 @@ def run_reference_arm(args, wl):
         if i >= args.warmup:
             vals.append(cb)
     fps = sum(v["fps"] for v in vals) / len(vals)
-    val = rays * fps / 1e6
+    unit = "fps" if raster else "Mrays/s"
+    val = fps if raster else rays * fps / 1e6
     cb = dict(vals[-1]); cb["value"] = val; cb["fps"] = fps
-    line = {"impl": "reference", "metric": "Mrays/s", "value": val, "unit": "Mrays/s", "fps": fps, "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": unit, "value": val, "unit": unit, "fps": fps, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / fps if fps else None,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "rays_per_frame": rays, "note": "reference CPU arm: no GPU involved"},
             "cpu_baseline": cb,
-            "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.time() - t0}
     print(json.dumps(line))
 
@@ -348,7 +360,9 @@ def run_b200_arm(args, wl):
         gpu.render_device(frame_for(s, full=(P == 1)), (full if P == 1 else shard).data_ptr(), None)
         per_frame.append(gpu.counters())
     gpu.set_counters(False)
-    keys = ("rays_primary", "rays_shadow", "rays_reflection", "rays_ao", "node_tests", "leaf_visits", "tri_tests")
+    raster = bool(wl.get("raster"))
+    keys = ("rays_primary", "rays_shadow", "rays_reflection", "rays_ao", "node_tests", "leaf_visits", "tri_tests",
+            "tris_setup", "spans", "z_tests", "z_passes")
     tot = {k: sum(c[k] for c in per_frame) for k in keys}
     if P > 1:
         t = torch.tensor([tot[k] for k in keys], dtype=torch.int64, device="cuda")
@@ -359,6 +373,7 @@ def run_b200_arm(args, wl):
     else:
         tot_all = tot_mine = tot
     rays_total = tot_all["rays_primary"] + tot_all["rays_shadow"] + tot_all["rays_reflection"] + tot_all["rays_ao"]
+    unit = "fps" if raster else "Mrays/s"
 
     # ---- device-timed run: W warm-up steps, then exactly K steps
     for s in range(Wm):
@@ -402,7 +417,7 @@ def run_b200_arm(args, wl):
         total_ms = float(t.item())
     ms_per_step = total_ms / K
     fps = 1000.0 / ms_per_step
-    value = rays_total / (total_ms / 1000.0) / 1e6
+    value = fps if raster else rays_total / (total_ms / 1000.0) / 1e6
 
     # ---- end-to-end through the public call with host buffers
     def time_e2e(pipelined):
@@ -426,12 +441,12 @@ def run_b200_arm(args, wl):
 
     e2e_s = time_e2e(True)
     e2e_sync_s = time_e2e(False) if P == 1 else e2e_s
-    e2e_value = rays_total / e2e_s / 1e6
+    e2e_value = K / e2e_s if raster else rays_total / e2e_s / 1e6
 
     if rank == 0:
         peak, peak_src = measured_peaks()
         # roofline of the dominant kernel (the ray-tracing kernel of THIS rank): algorithmic bytes / its duration
-        alg_bytes = algorithmic_bytes(tot_mine, W, (rows_per if P > 1 else H) * K)
+        alg_bytes = algorithmic_bytes(tot_mine, W, (rows_per if P > 1 else H) * K, raster)
         achieved = alg_bytes / (kern_total_ms / 1000.0) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -444,19 +459,23 @@ def run_b200_arm(args, wl):
         if P == 1 and not args.no_cpu_baseline:
             cpu = cpu_reference(wl, target_seconds=15.0, rays_per_frame=rays_total / K)
         line = {
-            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "fps": fps, "n_gpus": P, "steps": K, "warmup": Wm,
+            "metric": unit, "value": value, "unit": unit, "fps": fps, "n_gpus": P, "steps": K, "warmup": Wm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "camera": "reference -b orbit, one new frame per step",
-                       "rays_per_frame": rays_total / K, "l2": "flushed between timed steps (256 MiB write, outside the events)",
+                       "rays_per_frame": rays_total / K,
+                       "raster_per_frame": ({k: tot_all[k] / K for k in ("tris_setup", "spans", "z_tests", "z_passes")} if raster else None),
+                       "l2": "flushed between timed steps (256 MiB write, outside the events)",
                        "parallelism": "1 GPU" if P == 1 else f"row-cyclic sharding over {P} GPUs + 1 NCCL all-gather + de-interleave",
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "ray-tracing step = rt_rootcull_kernel + rt_primary_kernel (dominant; shades and casts the shadow rays itself)",
+                         "traffic": traffic,
+                         "kernel": ("rasteriser step = clears + ras_setup + ras_depth + ras_resolve (+ the 5 MLAA kernels)" if raster else
+                                    "ray-tracing step = rt_rootcull_kernel + rt_primary_kernel (dominant; shades and casts the shadow rays itself)"),
                          "kernel_ms": kern_total_ms / K,
                          "algorithmic_bytes_per_launch": alg_bytes / K, "peak_source": peak_src + " (of measured)"},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "fps": K / e2e_s,
+            "e2e": {"value": e2e_value, "unit": unit, "fps": K / e2e_s,
                     "h2d_bytes_per_step": C.sizeof(rb.Frame), "d2h_bytes_per_step": W * H * 4,
                     "fps_blocking_call": K / e2e_sync_s,
                     "note": ("b200r_render_async + b200r_wait with page-locked host frames: frame state in, XRGB frame out, per step; "
