@@ -65,6 +65,7 @@ struct b200r_ctx {
     unsigned long long* d_tileProf = nullptr; size_t tileProfTiles = 0; bool tileProfile = false; uint32_t lastTiles = 0;
     unsigned* d_shadowKeys = nullptr;
     uint32_t* d_mlaaScratch = nullptr; size_t mlaaWords = 0;
+    void* d_mlaaLines = nullptr; size_t mlaaLinesBytes = 0;
     bool counting = false;
     float last_total_ms = 0.f, last_dominant_ms = 0.f;
     uint32_t last_launches = 0;
@@ -151,7 +152,18 @@ int mlaa_on(b200r_ctx* ctx, uint32_t* d_frame, uint32_t width, uint32_t height, 
         ctx->mlaaWords = words;
     }
     int launches = 0;
-    CU(launch_mlaa(d_frame, ctx->d_mlaaScratch, (int)width, (int)height, ctx->numSMs, s, launches));
+    void* lines = nullptr;
+    if (!getenv("B200R_MLAA_SCAN")) {           // default: two-stage blending (all separation lines first, then the ordered blends)
+        const size_t need = mlaa_lines_bytes((int)width, (int)height);
+        if (ctx->mlaaLinesBytes < need) {
+            if (ctx->d_mlaaLines) cudaFree(ctx->d_mlaaLines);
+            ctx->d_mlaaLines = nullptr; ctx->mlaaLinesBytes = 0;
+            CU(cudaMalloc(&ctx->d_mlaaLines, need));
+            ctx->mlaaLinesBytes = need;
+        }
+        lines = ctx->d_mlaaLines;
+    }
+    CU(launch_mlaa(d_frame, ctx->d_mlaaScratch, (int)width, (int)height, ctx->numSMs, s, launches, lines));
     ctx->last_launches += (uint32_t)launches;
     return B200R_OK;
 }
@@ -361,7 +373,7 @@ void b200r_destroy(b200r_ctx* ctx)
     cudaFree(ctx->rt2.srays); cudaFree(ctx->rt2.sword); cudaFree(ctx->rt2.queue2); cudaFree(ctx->rt2.warpProf); cudaFree(ctx->rt2.sdon);
     cudaFree(ctx->d_tileCounter2);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
-    cudaFree(ctx->d_mlaaScratch); cudaFree(ctx->d_tileProf); cudaFree(ctx->rb.spans); cudaFree(ctx->rb.spanCount); cudaFree(ctx->rb.zkeys); cudaFree(ctx->d_shadowKeys);
+    cudaFree(ctx->d_mlaaScratch); cudaFree(ctx->d_mlaaLines); cudaFree(ctx->d_tileProf); cudaFree(ctx->rb.spans); cudaFree(ctx->rb.spanCount); cudaFree(ctx->rb.zkeys); cudaFree(ctx->d_shadowKeys);
     if (ctx->h_spanCount) cudaFreeHost(ctx->h_spanCount);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (auto& S : ctx->slot) {

@@ -229,15 +229,133 @@ mlaa_blend_kernel(uint32_t* fbi, const uint32_t* __restrict__ fb0, int resX, int
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Two-stage blending.  Everything process_line() decides - where the lines of a row are, their end points and split
+// heights - reads the immutable scratch copy only, so it does not depend on the blending order: mlaa_lines_kernel finds
+// ALL separation lines of the frame (both directions) at once, one thread per line, and stores a 32-byte record per
+// line in its row's list. The ordered part (8-row blocks, rows in order, even blocks before odd ones) is then left with
+// the in-place blends of the rows' records: no scan over the 98 % of pixels that carry no flag, and no serial walks
+// along the lines inside the ordered loop (4K frame: 4 x mlaa_blend_kernel = 1.07 ms of a 1.19 ms frame before).
+// ---------------------------------------------------------------------------------------------------------
+struct __align__(16) LineRec { int ui0, ui1, li0, li1; float uh0, uh1, lh0, lh1; };      // ui1 == -2: a one-pixel line at ui0
+
+__global__ void __launch_bounds__(256)
+mlaa_lines_kernel(const uint32_t* __restrict__ fb0, int resX, int resY, LineRec* __restrict__ recH, LineRec* __restrict__ recV,
+                  int* __restrict__ cntH, int* __restrict__ cntV, int* __restrict__ endH, int* __restrict__ endV, int capH, int capV)
+{
+    const int sz = resX * resY;
+    const int total = 2 * sz;
+    for (int gi = (int)(blockIdx.x * blockDim.x + threadIdx.x); gi < total; gi += (int)(gridDim.x * blockDim.x)) {
+        const int vertical = gi >= sz;
+        const int x = vertical ? gi - sz : gi;
+        unsigned fc; int resx, resy, stepy, stepx, row, k;
+        if (!vertical) { fc = HF; resx = resX; resy = resY; stepy = resX; stepx = 1; row = x / resX; k = x - row * resX; }
+        else { fc = VF; resx = resY; resy = resX; stepy = 1; stepx = resX; k = x / resX; row = x - k * resX; }
+        if (row >= resy - 1) continue;                                  // the last row / column is never a block row (MLAA.cc:556-557)
+        if (!(fb0[x] & fc)) continue;
+        if (k > 0 && (fb0[x - stepx] & fc)) continue;                   // not the first pixel of its run
+        const int yc = row * stepy;
+        int k1 = k;
+        while (k1 + 1 < resx && (fb0[yc + (k1 + 1) * stepx] & fc)) k1++;
+        atomicMax(vertical ? &endV[row] : &endH[row], k1);
+        int x0 = x; const int x1 = yc + k1 * stepx; int len = k1 - k + 1;
+        const int befor = row ? -stepy : 0, after = stepy;
+        LineRec r; r.ui0 = x0; r.ui1 = -2; r.li0 = r.li1 = -1; r.uh0 = r.uh1 = r.lh0 = r.lh1 = 0.f;
+        if (len != 1) {
+            if (x0 == yc) { x0 += stepx; len--; }
+            computeUpperBounds(r.ui0, r.ui1, r.uh0, r.uh1, fb0, fc, x0 - stepx, x1, len, stepx, befor, after, sz);
+            computeLowerBounds(r.li0, r.li1, r.lh0, r.lh1, fb0, fc, x0 - stepx, x1, len, stepx, after, sz);
+        }
+        const int slot = atomicAdd(vertical ? &cntV[row] : &cntH[row], 1);
+        if (slot < (vertical ? capV : capH)) (vertical ? recV + (size_t)row * capV : recH + (size_t)row * capH)[slot] = r;
+    }
+}
+
+__global__ void mlaa_lines_reset_kernel(int* __restrict__ cnt, int* __restrict__ lastEnd, int n)
+{
+    const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i < n) { cnt[i] = 0; lastEnd[i] = -1; }
+}
+
+// The ordered part: one CTA per 8-row (8-column) block of the given parity, rows in order, one thread per line record.
+__global__ void __launch_bounds__(256)
+mlaa_blend_lines_kernel(uint32_t* fbi, const uint32_t* __restrict__ fb0, int resX, int resY, int vertical, int yodd,
+                        const LineRec* __restrict__ rec, const int* __restrict__ cnt, const int* __restrict__ lastEnd, int cap)
+{
+    const int rows_per_job = 8;
+    int resx, resy, stepy, stepx;
+    if (!vertical) { resx = resX; resy = resY; stepy = resX; stepx = 1; }
+    else { resx = resY; resy = resX; stepy = 1; stepx = resX; }
+    const int jobindex = (int)blockIdx.x;
+    const int rfrst = (2 * jobindex + yodd) * rows_per_job;
+    int rlast = rfrst + rows_per_job;
+    if (rlast >= resy) rlast = resy - 1;
+    const int after = stepy;
+    const int sz = resX * resY;
+    for (int row = rfrst; row < rlast; row++) {
+        const int befor = row ? -stepy : 0;
+        const int n = min(cnt[row], cap);
+        const LineRec* rr = rec + (size_t)row * cap;
+        for (int i = (int)threadIdx.x; i < n; i += (int)blockDim.x) {
+            const LineRec r = rr[i];
+            if (r.ui1 == -2) { blend_one_cell(fbi, r.ui0, after); continue; }
+            bool done = false;
+            if (r.ui0 != -1 && r.li1 != -1 && r.ui0 < r.li1) { blendInterval(fbi, r.ui0, r.li1, r.uh0, r.lh1, stepx, after, false); done = true; }
+            if (r.li0 != -1 && r.ui1 != -1 && r.li0 < r.ui1) { blendInterval(fbi, r.li0, r.ui1, r.lh0, r.uh1, stepx, befor, false); done = true; }
+            if (!done) {
+                if (r.ui0 != -1 && r.ui1 != -1 && r.ui0 < r.ui1) blendInterval(fbi, r.ui0, r.ui1, r.uh0, r.uh1, stepx, after, true);
+                if (r.li0 != -1 && r.li1 != -1 && r.li0 < r.li1) blendInterval(fbi, r.li0, r.li1, r.lh0, r.lh1, stepx, befor, true);
+            }
+        }
+        __syncthreads();
+        // the SSE scan quirk of the horizontal search (see mlaa_blend_kernel), applied after all lines of this row
+        if (!vertical && threadIdx.x == 0) {
+            const int kEnd = lastEnd[row];
+            if (kEnd >= 0 && (kEnd == resx - 4 || kEnd == resx - 3)) {
+                const int base = row * stepy + resx;
+                for (int q = 0; q < 4; q++)
+                    if (fb0[base + q] & HF) {
+                        if (base + q + after < sz) blend_one_cell(fbi, base + q, after);
+                        break;
+                    }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
-cudaError_t launch_mlaa(uint32_t* d_frame, uint32_t* d_scratch, int resX, int resY, int numSMs, cudaStream_t st, int& launches)
+size_t mlaa_lines_bytes(int resX, int resY)
+{
+    const size_t capH = (size_t)resX / 2 + 1, capV = (size_t)resY / 2 + 1;
+    return ((size_t)resY * capH + (size_t)resX * capV) * sizeof(LineRec) + 2 * ((size_t)resX + resY) * sizeof(int);
+}
+
+cudaError_t launch_mlaa(uint32_t* d_frame, uint32_t* d_scratch, int resX, int resY, int numSMs, cudaStream_t st, int& launches,
+                        void* d_lines)
 {
     mlaa_find_fragments_kernel<<<numSMs * 4, 256, 0, st>>>(d_frame, d_scratch, resX, resY);
     const int n_hscan_jobs = (resY / 8) + ((resY % 8) ? 1 : 0);
     const int n_vscan_jobs = (resX / 8) + ((resX % 8) ? 1 : 0);
     // job list halves (MLAA.cc:545-552): the first scanjobs/2 jobs are the even blocks, the rest the odd blocks
     const int h0 = n_hscan_jobs / 2, h1 = n_hscan_jobs - h0, v0 = n_vscan_jobs / 2, v1 = n_vscan_jobs - v0;
+    if (d_lines) {
+        // two-stage path: all lines of the frame first (order-independent), then the ordered in-place blends
+        const int capH = resX / 2 + 1, capV = resY / 2 + 1;
+        LineRec* recH = reinterpret_cast<LineRec*>(d_lines);
+        LineRec* recV = recH + (size_t)resY * capH;
+        int* cntH = reinterpret_cast<int*>(recV + (size_t)resX * capV);
+        int* cntV = cntH + resY; int* endH = cntV + resX; int* endV = endH + resY;
+        mlaa_lines_reset_kernel<<<(resX + resY + 255) / 256, 256, 0, st>>>(cntH, endH, resX + resY);   // cntH|cntV and endH|endV are contiguous
+        mlaa_lines_kernel<<<numSMs * 8, 256, 0, st>>>(d_scratch, resX, resY, recH, recV, cntH, cntV, endH, endV, capH, capV);
+        if (h0 > 0) mlaa_blend_lines_kernel<<<h0, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 0, 0, recH, cntH, endH, capH);
+        if (h1 > 0) mlaa_blend_lines_kernel<<<h1, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 0, 1, recH, cntH, endH, capH);
+        if (v0 > 0) mlaa_blend_lines_kernel<<<v0, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 1, 0, recV, cntV, endV, capV);
+        if (v1 > 0) mlaa_blend_lines_kernel<<<v1, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 1, 1, recV, cntV, endV, capV);
+        launches += 7;
+        return cudaGetLastError();
+    }
     if (h0 > 0) mlaa_blend_kernel<<<h0, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 0, 0);
     if (h1 > 0) mlaa_blend_kernel<<<h1, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 0, 1);
     if (v0 > 0) mlaa_blend_kernel<<<v0, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 1, 0);

@@ -50,7 +50,10 @@ struct WireBuffers {
 cudaError_t launch_wire_count(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, WireBuffers& wb, cudaStream_t st, int& launches);
 cudaError_t launch_wire_emit(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, WireBuffers& wb, int numSMs, cudaStream_t st,
                              int& launches);
-cudaError_t launch_mlaa(uint32_t* d_frame, uint32_t* d_scratch, int resX, int resY, int numSMs, cudaStream_t st, int& launches);
+// d_lines: mlaa_lines_bytes(resX, resY) bytes of scratch for the two-stage path (line records per row); nullptr = row-scanning kernels
+cudaError_t launch_mlaa(uint32_t* d_frame, uint32_t* d_scratch, int resX, int resY, int numSMs, cudaStream_t st, int& launches,
+                        void* d_lines);
+size_t mlaa_lines_bytes(int resX, int resY);
 cudaError_t launch_division_selftest(unsigned long long samples, uint32_t seed, unsigned long long* d_mismatches,
                                      float* d_firstBad, int numSMs, cudaStream_t stream);
 cudaError_t launch_deinterleave(const uint32_t* gathered, uint32_t* frame, uint32_t W, uint32_t H, uint32_t P,
