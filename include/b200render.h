@@ -171,6 +171,18 @@ int  b200r_mlaa_device(b200r_ctx* ctx, void* dev_xrgb, uint32_t width, uint32_t 
 int  b200r_deinterleave_device(b200r_ctx* ctx, const void* dev_gathered, void* dev_frame,
                                uint32_t width, uint32_t height, uint32_t n_shards, void* cuda_stream);
 
+/* Replaces: CreateBVH + CreateCFBVH (src/BVH.cc:96-371 scalar path, src/Raytracer.cc:651-718) ON THE DEVICE: the SAH
+ * build as level-synchronous kernels (csrc/bvh_steps.h, csrc/cuda/bvh_build.cu) producing the same tree bit for bit - the
+ * nodes/tri_idx written here are byte-identical to the reference's .bvh cache content. nodes_out needs room for
+ * 2*n_tris + 1 nodes, tri_idx_out for n_tris indices. Does not change the uploaded scene: pass the result to
+ * b200r_upload_scene (and/or write it as a cache). Fails if the tree is deeper than the reference's BVH_STACK_SIZE. */
+int  b200r_build_bvh(b200r_ctx* ctx, const b200r_vertex* verts, uint32_t n_verts, const b200r_tri* tris, uint32_t n_tris,
+                     b200r_bvhnode* nodes_out, uint32_t nodes_cap, int32_t* tri_idx_out, uint32_t* n_nodes, int32_t* depth);
+/* Test hook (no device needed): the very same per-item step functions run in plain loops on the host. Not a build path. */
+int  b200r_selftest_bvh_steps_host(const b200r_vertex* verts, uint32_t n_verts, const b200r_tri* tris, uint32_t n_tris,
+                                   b200r_bvhnode* nodes_out, uint32_t nodes_cap, int32_t* tri_idx_out,
+                                   uint32_t* n_nodes, int32_t* depth);
+
 /* Numerics self-test: the slab test's shared-reciprocal divide (DESIGN.md "division") against the compiler's IEEE
  * divide on `samples` random operand pairs drawn from the whole domain in which the fast path is used.
  * *mismatches must come back 0. first_bad (optional) receives {a, d, a/d, fast} of the first mismatch. */

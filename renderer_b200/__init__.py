@@ -108,6 +108,23 @@ class Scene:
         n = L.b200r_scene_nodes(self._h, C.byref(nn)); i = L.b200r_scene_tri_idx(self._h, C.byref(ni))
         return v, nv.value, t, nt.value, n, nn.value, i, ni.value
 
+    def _built_bvh_bytes(self, call):
+        v, nv, t, nt, _, _, _, _ = self.raw()
+        nodes = (_abi.BvhNode * (2 * nt + 1))()
+        idx = (C.c_int32 * nt)()
+        nn, depth = C.c_uint32(), C.c_int32()
+        call(v, nv, t, nt, nodes, 2 * nt + 1, idx, C.byref(nn), C.byref(depth))
+        head = np.array([nn.value, nt], dtype=np.uint32).tobytes()
+        return head + bytes(memoryview(nodes))[:nn.value * C.sizeof(_abi.BvhNode)] + bytes(memoryview(idx)), depth.value
+
+    def bvh_bytes_from_steps_on_host(self):
+        """(.bvh cache bytes, depth) produced by the device build's step functions run in plain loops on the host (test hook)."""
+        return self._built_bvh_bytes(lambda *a: _check(lib().b200r_selftest_bvh_steps_host(*a)))
+
+    def bvh_bytes_from_device_build(self, renderer):
+        """(.bvh cache bytes, depth) produced by b200r_build_bvh: the SAH build as CUDA kernels."""
+        return self._built_bvh_bytes(lambda *a: _check(lib().b200r_build_bvh(renderer._ctx, *a), renderer._ctx))
+
     def bvh_bytes(self):
         """The flattened BVH in the reference's .bvh cache layout (Raytracer.cc:747-753)."""
         nodes, nn = self._arr(lib().b200r_scene_nodes, _abi.BvhNode)

@@ -73,6 +73,10 @@ SYMBOLS = {
     "b200r_deinterleave_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                             C.c_uint32, C.c_void_p]),
     "b200r_selftest_division": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, P(C.c_uint64), P(C.c_float)]),
+    "b200r_build_bvh": (C.c_int, [C.c_void_p, P(Vertex), C.c_uint32, P(Tri), C.c_uint32, P(BvhNode), C.c_uint32,
+                                  P(C.c_int32), P(C.c_uint32), P(C.c_int32)]),
+    "b200r_selftest_bvh_steps_host": (C.c_int, [P(Vertex), C.c_uint32, P(Tri), C.c_uint32, P(BvhNode), C.c_uint32,
+                                                P(C.c_int32), P(C.c_uint32), P(C.c_int32)]),
     "b200r_set_tile_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "b200r_get_tile_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, P(C.c_uint32)]),
     "b200r_set_counters": (C.c_int, [C.c_void_p, C.c_int]),

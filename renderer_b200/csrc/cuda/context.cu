@@ -5,6 +5,7 @@
 // if CUDA is unavailable b200r_init() fails and nothing can be rendered.
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
@@ -714,6 +715,28 @@ int b200r_deinterleave_device(b200r_ctx* ctx, const void* dev_gathered, void* de
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     CU(launch_deinterleave((const uint32_t*)dev_gathered, (uint32_t*)dev_frame, width, height, n_shards, ctx->numSMs, s));
     if (!cuda_stream) CU(cudaStreamSynchronize(s));
+    return B200R_OK;
+}
+
+int b200r_build_bvh(b200r_ctx* ctx, const b200r_vertex* verts, uint32_t n_verts, const b200r_tri* tris, uint32_t n_tris,
+                    b200r_bvhnode* nodes_out, uint32_t nodes_cap, int32_t* tri_idx_out, uint32_t* n_nodes, int32_t* depth)
+{
+    if (!ctx) return fail(nullptr, B200R_EINVAL, "NULL ctx");
+    if (!verts || !tris || !nodes_out || !tri_idx_out || !n_nodes || !depth || !n_verts || !n_tris)
+        return fail(ctx, B200R_EINVAL, "b200r_build_bvh: bad argument");
+    static_assert(sizeof(b200r_vertex) % sizeof(float) == 0 && offsetof(b200r_vertex, pos) == 0, "vertex positions lead the record");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<uint32_t> idx(3 * (size_t)n_tris);
+    for (uint32_t i = 0; i < n_tris; i++) {
+        if (tris[i].a >= n_verts || tris[i].b >= n_verts || tris[i].c >= n_verts) return fail(ctx, B200R_EINVAL, "b200r_build_bvh: vertex index out of range");
+        idx[3 * (size_t)i] = tris[i].a; idx[3 * (size_t)i + 1] = tris[i].b; idx[3 * (size_t)i + 2] = tris[i].c;
+    }
+    int launches = 0;
+    // levels <= BVH_STACK_SIZE: the reference refuses deeper trees (Raytracer.cc:711-717)
+    CU(launch_bvh_build(verts[0].pos, (int)(sizeof(b200r_vertex) / sizeof(float)), n_verts, idx.data(), n_tris, nodes_out, nodes_cap,
+                        tri_idx_out, n_nodes, depth, B200R_BVH_STACK_SIZE, ctx->stream, launches));
+    ctx->last_launches = (uint32_t)launches;
+    if (*depth < 0) return fail(ctx, B200R_EDEPTH, "Max depth of BVH exceeds BVH_STACK_SIZE");
     return B200R_OK;
 }
 

@@ -54,6 +54,11 @@ cudaError_t launch_wire_emit(const DeviceScene& sc, const FrameParams& fp, uint3
 cudaError_t launch_mlaa(uint32_t* d_frame, uint32_t* d_scratch, int resX, int resY, int numSMs, cudaStream_t st, int& launches,
                         void* d_lines);
 size_t mlaa_lines_bytes(int resX, int resY);
+// SAH BVH build on the device (bvh_build.cu): host arrays in (vertex positions with a float stride, 3 indices per triangle), the
+// flattened tree out (32-byte nodes in DFS pre-order + the triangle index list). *depth < 0: deeper than maxLevels - 1.
+cudaError_t launch_bvh_build(const float* h_vertPos, int strideFloats, uint32_t nVerts, const uint32_t* h_idx, uint32_t nTris,
+                             void* h_nodes_out, uint32_t nodesCap, int32_t* h_order_out, uint32_t* nNodes, int32_t* depth,
+                             int maxLevels, cudaStream_t st, int& launches);
 cudaError_t launch_division_selftest(unsigned long long samples, uint32_t seed, unsigned long long* d_mismatches,
                                      float* d_firstBad, int numSMs, cudaStream_t stream);
 cudaError_t launch_deinterleave(const uint32_t* gathered, uint32_t* frame, uint32_t W, uint32_t H, uint32_t P,

@@ -21,6 +21,20 @@ def test_bvh_is_byte_identical_to_reference_cache(rb, pyport, model):
     assert 0 <= s.bvh_depth < 32
 
 
+@pytest.mark.parametrize("model", ["single.ply", "square.ply", "box-and-plane.ply", "torus.ply", "sphere.ply", "x-wing.ply", "tie.ply",
+                                   "trainColor.tri", "dragon_vis.ply"])
+def test_device_bvh_build_steps_reproduce_the_reference_tree(rb, pyport, model):
+    """csrc/bvh_steps.h - the per-item functions the CUDA build kernels are made of - run level by level in plain loops:
+    the resulting .bvh bytes equal the cache the reference wrote (and therefore the recursive host builder's)."""
+    path = pyport.model_path(model)
+    if not os.path.exists(path):
+        pytest.skip("model not staged")
+    s = rb.Scene(path)
+    got, depth = s.bvh_bytes_from_steps_on_host()
+    assert hashlib.sha256(got).hexdigest() == INDEX["_bvh_sha256"][model]
+    assert 0 <= depth < 32
+
+
 def test_bvh_cache_roundtrip_and_interop(rb, pyport, tmp_path):
     path = pyport.model_path("torus.ply")
     if not os.path.exists(path):
