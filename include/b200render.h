@@ -212,6 +212,8 @@ void b200r_scene_free(b200r_scene* s);
  * (Raytracer.cc:651-718) and writes the cache (same on-disk format). cache_path may be NULL. */
 int  b200r_scene_build_bvh(b200r_scene* s, const char* cache_path, int force_rebuild);
 
+/* The same, with the build on the device (b200r_build_bvh) instead of the host: identical tree, identical cache file. */
+int  b200r_scene_build_bvh_device(b200r_scene* s, b200r_ctx* ctx, const char* cache_path, int force_rebuild);
 const b200r_vertex*  b200r_scene_vertices(const b200r_scene* s, uint32_t* n);
 const b200r_tri*     b200r_scene_tris(const b200r_scene* s, uint32_t* n);
 const b200r_bvhnode* b200r_scene_nodes(const b200r_scene* s, uint32_t* n);

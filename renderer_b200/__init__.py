@@ -76,6 +76,12 @@ class Scene:
                                             1 if forceRecalc else 0))
         return self
 
+    def UpdateBoundingVolumeHierarchyOnDevice(self, renderer, cache_path=None, forceRecalc=False):
+        """The same, with CreateBVH/CreateCFBVH run as CUDA kernels (b200r_build_bvh): same tree, same cache file."""
+        _check(lib().b200r_scene_build_bvh_device(self._h, renderer._ctx, os.fsencode(cache_path) if cache_path else None,
+                                                   1 if forceRecalc else 0), renderer._ctx)
+        return self
+
     def _arr(self, fn, ctype):
         n = C.c_uint32()
         p = fn(self._h, C.byref(n))

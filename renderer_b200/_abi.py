@@ -86,6 +86,7 @@ SYMBOLS = {
     "b200r_scene_load": (C.c_int, [C.c_char_p, P(C.c_void_p)]),
     "b200r_scene_free": (None, [C.c_void_p]),
     "b200r_scene_build_bvh": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "b200r_scene_build_bvh_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]),
     "b200r_scene_vertices": (P(Vertex), [C.c_void_p, P(C.c_uint32)]),
     "b200r_scene_tris": (P(Tri), [C.c_void_p, P(C.c_uint32)]),
     "b200r_scene_nodes": (P(BvhNode), [C.c_void_p, P(C.c_uint32)]),

@@ -54,6 +54,25 @@ int b200r_scene_build_bvh(b200r_scene* s, const char* cache_path, int force_rebu
     return B200R_OK;
 }
 
+// Scene::UpdateBoundingVolumeHierarchy with the build itself on the device: cache hit -> as above; else b200r_build_bvh
+// (CUDA kernels, same tree) fills the scene's node / index arrays and the cache file is written in the reference's format.
+int b200r_scene_build_bvh_device(b200r_scene* s, b200r_ctx* ctx, const char* cache_path, int force_rebuild)
+{
+    if (!s || !ctx) { b200r::set_global_error("b200r_scene_build_bvh_device: NULL argument"); return B200R_EINVAL; }
+    if (!force_rebuild && cache_path && s->s.read_bvh_cache(cache_path)) return B200R_OK;
+    const uint32_t nt = (uint32_t)s->s.tris.size();
+    std::vector<b200r_bvhnode> nodes(2 * (size_t)nt + 1);
+    std::vector<int32_t> idx(nt);
+    uint32_t nn = 0; int32_t depth = -1;
+    const int rc = b200r_build_bvh(ctx, s->s.verts.data(), (uint32_t)s->s.verts.size(), s->s.tris.data(), nt, nodes.data(),
+                                   (uint32_t)nodes.size(), idx.data(), &nn, &depth);
+    if (rc) return rc;
+    nodes.resize(nn);
+    s->s.nodes.swap(nodes); s->s.tri_idx.swap(idx); s->s.bvh_depth = depth;
+    if (cache_path) s->s.write_bvh_cache(cache_path);   // silently ignored on failure, like the reference
+    return B200R_OK;
+}
+
 const b200r_vertex* b200r_scene_vertices(const b200r_scene* s, uint32_t* n)
 { if (n) *n = (uint32_t)s->s.verts.size(); return s->s.verts.data(); }
 const b200r_tri* b200r_scene_tris(const b200r_scene* s, uint32_t* n)

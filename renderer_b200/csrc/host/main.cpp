@@ -47,7 +47,7 @@ static void usage()
                     "       9 : raytracing, with shadows and reflections\n"
                     "       0 : raytracing, with shadows, reflections and anti-aliasing\n"
                     "  --width W --height H --no-reflections --no-shadows --ao N --mlaa\n"
-                    "  --dump PREFIX --frames a,b,c --device D\n");
+                    "  --dump PREFIX --frames a,b,c --device D --host-bvh\n");
     exit(0);
 }
 
@@ -64,6 +64,7 @@ int main(int argc, char* argv[])
     unsigned benchmarkFrames = 100;
     unsigned W = 800, H = 600, flags = B200R_F_DEFAULT, ao = 0;
     int device = 0;
+    bool hostBvh = false;
     std::string dumpPrefix;
     std::set<unsigned> dumpFrames;
 
@@ -71,7 +72,7 @@ int main(int argc, char* argv[])
                                 {"no-reflections", no_argument, 0, 1002}, {"no-shadows", no_argument, 0, 1003},
                                 {"ao", required_argument, 0, 1004}, {"mlaa", no_argument, 0, 1005},
                                 {"dump", required_argument, 0, 1006}, {"frames", required_argument, 0, 1007},
-                                {"device", required_argument, 0, 1008}, {0, 0, 0, 0}};
+                                {"device", required_argument, 0, 1008}, {"host-bvh", no_argument, 0, 1009}, {0, 0, 0, 0}};
     int c;
     opterr = 0;
     while ((c = getopt_long(argc, argv, "hbrwn:m:", longopts, nullptr)) != -1) switch (c) {
@@ -93,6 +94,7 @@ int main(int argc, char* argv[])
         case 1006: dumpPrefix = optarg; break;
         case 1007: { char* p = optarg; while (*p) { dumpFrames.insert((unsigned)strtoul(p, &p, 10)); if (*p == ',') p++; else break; } } break;
         case 1008: device = atoi(optarg); break;
+        case 1009: hostBvh = true; break;
         case '?': fprintf(stderr, "No such option (%c)\n", (char)optopt); usage(); break;
         default: break;
     }
@@ -105,16 +107,18 @@ int main(int argc, char* argv[])
     b200r_scene_vertices(scene, &nv); b200r_scene_tris(scene, &nt);
     printf("Vertexes: %u Triangles: %u\n", nv, nt);
     const bool raytrace = (mode == B200R_MODE_RAYTRACE || mode == B200R_MODE_RAYTRACE_AA);
+    b200r_ctx* ctx = nullptr;
+    if (b200r_init(device, &ctx)) { fprintf(stderr, "%s\n", b200r_last_error(nullptr)); return 1; }
     if (raytrace) {
         puts("Creating BVH... please wait...");
         const std::string cache = std::string(fname) + ".bvh";      // same cache file as the reference
         const double t0 = now_ms();
-        if (b200r_scene_build_bvh(scene, cache.c_str(), 0)) { fprintf(stderr, "%s\n", b200r_last_error(nullptr)); return 1; }
+        // the SAH build runs on the device (same tree, same cache file); --host-bvh keeps it on the host
+        const int rc = hostBvh ? b200r_scene_build_bvh(scene, cache.c_str(), 0) : b200r_scene_build_bvh_device(scene, ctx, cache.c_str(), 0);
+        if (rc) { fprintf(stderr, "%s\n", b200r_last_error(hostBvh ? nullptr : ctx)); return 1; }
         printf("BVH ready in %.2f seconds (depth %d)\n", (now_ms() - t0) / 1000., b200r_scene_bvh_depth(scene));
     }
 
-    b200r_ctx* ctx = nullptr;
-    if (b200r_init(device, &ctx)) { fprintf(stderr, "%s\n", b200r_last_error(nullptr)); return 1; }
     if (b200r_upload_scene_handle(ctx, scene)) { fprintf(stderr, "%s\n", b200r_last_error(ctx)); return 1; }
 
     const unsigned nLights = useTwoLights ? 2 : 1;

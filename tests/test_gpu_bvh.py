@@ -40,3 +40,13 @@ def test_device_built_bvh_renders_the_same_frame(rb, pyport, load_scene, gpu):
     assert got_bytes == s.bvh_bytes()
     print(f"device BVH build of chessboard.tri: {dt * 1e3:.1f} ms wall (second call, incl. copies)")
     assert np.array_equal(gpu.render(f), want)
+
+
+def test_scene_handle_builds_on_device_and_writes_the_reference_cache(rb, pyport, gpu, tmp_path):
+    """b200r_scene_build_bvh_device: no cache -> device build + cache file with the reference's bytes; second call reads it."""
+    path = pyport.model_path("trainColor.tri")
+    cache = str(tmp_path / "trainColor.tri.bvh")
+    a = rb.Scene(path).UpdateBoundingVolumeHierarchyOnDevice(gpu, cache)
+    assert hashlib.sha256(open(cache, "rb").read()).hexdigest() == INDEX["_bvh_sha256"]["trainColor.tri"]
+    b = rb.Scene(path).UpdateBoundingVolumeHierarchy(cache)           # the host path reads the same cache
+    assert a.bvh_bytes() == b.bvh_bytes() and a.bvh_depth == b.bvh_depth
