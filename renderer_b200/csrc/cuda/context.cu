@@ -62,6 +62,7 @@ struct b200r_ctx {
     RtBuffers rt{};
     WireBuffers wb{};
     size_t zkey_pixels = 0;
+    float4* d_attrs = nullptr; size_t attr_pixels = 0;
     unsigned* h_spanCount = nullptr;          // pinned
     unsigned long long* d_tileProf = nullptr; size_t tileProfTiles = 0; bool tileProfile = false; uint32_t lastTiles = 0;
     unsigned* d_shadowKeys = nullptr;
@@ -255,6 +256,15 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
             CU(cudaMalloc((void**)&ctx->rb.zkeys, px * 8));
             ctx->zkey_pixels = px;
         }
+        if (fp.mode >= B200R_MODE_PHONG && !getenv("B200R_RASTER_INLINE_SHADE")) {      // per-pixel lighting pass (default)
+            if (ctx->attr_pixels < px) {
+                if (ctx->d_attrs) cudaFree(ctx->d_attrs);
+                ctx->d_attrs = nullptr; ctx->attr_pixels = 0;
+                CU(cudaMalloc((void**)&ctx->d_attrs, px * 32));
+                ctx->attr_pixels = px;
+            }
+            ctx->rb.attrs = ctx->d_attrs;
+        } else ctx->rb.attrs = nullptr;
         if (!ctx->rb.spans) {
             ctx->rb.spanCapacity = 1u << 20;
             CU(cudaMalloc((void**)&ctx->rb.spans, (size_t)ctx->rb.spanCapacity * 80));
@@ -374,7 +384,7 @@ void b200r_destroy(b200r_ctx* ctx)
     cudaFree(ctx->rt2.srays); cudaFree(ctx->rt2.sword); cudaFree(ctx->rt2.queue2); cudaFree(ctx->rt2.warpProf); cudaFree(ctx->rt2.sdon);
     cudaFree(ctx->d_tileCounter2);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
-    cudaFree(ctx->d_mlaaScratch); cudaFree(ctx->d_mlaaLines); cudaFree(ctx->d_tileProf); cudaFree(ctx->rb.spans); cudaFree(ctx->rb.spanCount); cudaFree(ctx->rb.zkeys); cudaFree(ctx->d_shadowKeys);
+    cudaFree(ctx->d_attrs); cudaFree(ctx->d_mlaaScratch); cudaFree(ctx->d_mlaaLines); cudaFree(ctx->d_tileProf); cudaFree(ctx->rb.spans); cudaFree(ctx->rb.spanCount); cudaFree(ctx->rb.zkeys); cudaFree(ctx->d_shadowKeys);
     if (ctx->h_spanCount) cudaFreeHost(ctx->h_spanCount);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (auto& S : ctx->slot) {

@@ -435,6 +435,57 @@ ras_resolve_kernel(DeviceScene sc, FrameParams fp, const uint32_t* __restrict__ 
     if (count && wins) atomicAdd(&ctr->v[C_Z_PASSES], wins);
 }
 
+// ---------------------------------------------------------------- K3 split in two for per-pixel Phong (modes 6-8)
+// ras_resolve_kernel shades inside the span walk: one thread per span, spans of ~5 pixels of which a part wins, ~300
+// instructions per shaded pixel -> 9.8 of 32 lanes active per instruction (ncu, profiles/r01h_ncu_c4.txt). Every pixel has at
+// most one winning fragment, so the walk only has to leave the winner's interpolants in a per-pixel slot (32 bytes) ...
+__global__ void __launch_bounds__(256)
+ras_resolve_attr_kernel(FrameParams fp, const uint32_t* __restrict__ spans, const unsigned* __restrict__ spanCount,
+                        unsigned spanCapacity, const unsigned long long* __restrict__ zkeys, float4* __restrict__ attrs,
+                        DeviceCounters* __restrict__ ctr, int count)
+{
+    constexpr int N = 8;
+    const unsigned n = min(*spanCount, spanCapacity);
+    const int W = (int)fp.W;
+    unsigned long long wins = 0;
+    for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        uint32_t tri; int y; bool single, empty; FPd<N> L, R;
+        load_span<N>(spans, s, tri, y, single, empty, L, R);
+        if (empty) continue;
+        const size_t rowOff = (size_t)((y - (int)fp.row_first) / (int)fp.row_step) * W;
+        walk_span<N>(W, single, L, R, [&](int x, const FPd<N>& v) {
+            const float z = v.v[3];
+            if (z > 0.f && zkeys[rowOff + x] == depth_key(z, tri)) {
+                float4* a = attrs + 2 * (rowOff + x);
+                a[0] = make_float4(v.v[1], v.v[2], v.v[3], v.v[4]);
+                a[1] = make_float4(v.v[5], v.v[6], v.v[7], 0.f);
+                wins++;
+            }
+        });
+    }
+    if (count && wins) atomicAdd(&ctr->v[C_Z_PASSES], wins);
+}
+// ... and the lighting runs one thread per PIXEL (neighbouring pixels are covered or not together; this pass also writes the
+// black of the uncovered ones, i.e. it is Screen::ClearScreen too). Same shade_fragment(), same inputs: same pixels.
+template <int LM>
+__global__ void __launch_bounds__(256)
+ras_shade_pixels_kernel(DeviceScene sc, FrameParams fp, const unsigned long long* __restrict__ zkeys, const float4* __restrict__ attrs,
+                        uint32_t* __restrict__ out, size_t nPixels)
+{
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < nPixels; p += (size_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = zkeys[p];
+        uint32_t c = 0u;
+        if (key) {
+            const uint32_t tri = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+            const float4 a0 = __ldg(attrs + 2 * p), a1 = __ldg(attrs + 2 * p + 1);
+            FPd<8> v;
+            v.v[0] = 0.f; v.v[1] = a0.x; v.v[2] = a0.y; v.v[3] = a0.z; v.v[4] = a0.w; v.v[5] = a1.x; v.v[6] = a1.y; v.v[7] = a1.z;
+            c = shade_fragment<8, LM>(sc, fp, v, tri);
+        }
+        out[p] = c;
+    }
+}
+
 // ---------------------------------------------------------------- points (modes 1, 2)
 __device__ __forceinline__ bool project_point(const FrameParams& fp, const V3& p, int& x, int& y)
 {
@@ -570,6 +621,15 @@ cudaError_t run_raster_mode(const DeviceScene& sc, const FrameParams& fp, uint32
     ras_setup_kernel<MODE><<<(sc.n_tris + tb - 1) / tb, tb, 0, st>>>(sc, fp, rb.spans, rb.spanCount, rb.spanCapacity, d_ctr, count ? 1 : 0);
     const int grid = numSMs * 8;
     ras_depth_kernel<N><<<grid, 256, 0, st>>>(fp, rb.spans, rb.spanCount, rb.spanCapacity, rb.zkeys, d_ctr, count ? 1 : 0);
+    if constexpr (N == 8) {
+        if (rb.attrs) {
+            const size_t px = (size_t)fp.W * fp.n_rows;
+            ras_resolve_attr_kernel<<<grid, 256, 0, st>>>(fp, rb.spans, rb.spanCount, rb.spanCapacity, rb.zkeys, rb.attrs, d_ctr, count ? 1 : 0);
+            ras_shade_pixels_kernel<LM><<<numSMs * 16, 256, 0, st>>>(sc, fp, rb.zkeys, rb.attrs, d_out, px);
+            launches += 4;
+            return cudaGetLastError();
+        }
+    }
     ras_resolve_kernel<N, LM><<<grid, 256, 0, st>>>(sc, fp, rb.spans, rb.spanCount, rb.spanCapacity, rb.zkeys, d_out, d_ctr, count ? 1 : 0);
     launches += 3;
     return cudaGetLastError();
@@ -581,7 +641,9 @@ cudaError_t launch_raster(const DeviceScene& sc, const FrameParams& fp, uint32_t
                           DeviceCounters* d_ctr, bool count, int numSMs, cudaStream_t st, int& launches)
 {
     const size_t px = (size_t)fp.W * fp.n_rows;
-    cudaError_t e = cudaMemsetAsync(d_out, 0, px * 4, st);                       // Screen::ClearScreen
+    cudaError_t e = cudaSuccess;
+    const bool perPixelShade = fp.mode >= B200R_MODE_PHONG && fp.mode <= B200R_MODE_PHONG_SOFTSHADOWMAPS && rb.attrs;
+    if (!perPixelShade) e = cudaMemsetAsync(d_out, 0, px * 4, st);               // Screen::ClearScreen (else: ras_shade_pixels_kernel writes every pixel)
     if (e != cudaSuccess) return e;
     if (fp.mode == B200R_MODE_POINTS) {
         points_vertices_kernel<<<(sc.n_verts + 255) / 256, 256, 0, st>>>(sc, fp, d_out);

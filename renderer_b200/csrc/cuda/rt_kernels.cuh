@@ -37,6 +37,7 @@ struct RasterBuffers {
     unsigned* spanCount = nullptr;
     unsigned spanCapacity = 0;
     unsigned long long* zkeys = nullptr;
+    float4* attrs = nullptr;                   // modes 6-8: the winning fragment's interpolants per pixel (2 x float4); nullptr = shade inside the span walk
 };
 cudaError_t launch_raster(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, RasterBuffers& rb,
                           DeviceCounters* d_ctr, bool count, int numSMs, cudaStream_t st, int& launches);
