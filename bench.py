@@ -40,6 +40,13 @@ WORKLOADS = {
 }
 
 
+# ray-traced frames in flight (bench protocol "pipelined" and the e2e leg); B200R_BENCH_DEPTH / B200R_E2E_DEPTH override.
+# Measured on one B200 (profiles/README.md, session r01i): 2 frames in flight 3620 fps, 3: 3370, 4: 3290, 6: 2990 - on one GPU a
+# third frame only adds contention; with the frame's rows dealt over N GPUs each rank's kernel is short and latency-bound, so
+# more frames are needed to fill it.
+DEFAULT_DEPTH = 2
+
+
 def algorithmic_bytes(c, W, rows, raster=False):
     """32 B per node popped (inner test or leaf visit), 68 B per triangle tested (4-B index +
     64 B of plane/edge data) + 16 B (centre + twoSided) because culling is on for every ray, + 4 B per pixel.
@@ -334,7 +341,7 @@ def run_b200_arm(args, wl):
         (gpu.wait() before the clock stops); pipelined=False times the blocking b200r_render instead."""
         if P == 1:
             if pipelined:
-                gpu.render_async(frame_for(step), host_ring[step % 3])
+                gpu.render_async(frame_for(step), host_ring[step % len(host_ring)])
             else:
                 gpu.render(frame_for(step), out=host_np)
         else:
@@ -415,12 +422,84 @@ def run_b200_arm(args, wl):
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
-    ms_per_step = total_ms / K
+    serial_ms_per_step = total_ms / K
+    serial_launches = launches
+
+    # ---- the same K steps with frames IN FLIGHT (the product's mode for independent frames, renderer_b200.dist.FramePipeline):
+    # frame i+1's kernels start while frame i's last long rays are still being walked, and (N > 1) the all-gather of frame i is
+    # on the wire while the next frames render. The L2 flush stays: one > L2 write enqueued on the frame's stream before every
+    # frame, INSIDE the timed region. One start event before the first flush, one end event after every stream has joined.
+    depth = int(os.environ.get("B200R_BENCH_DEPTH", "0")) or (0 if raster else DEFAULT_DEPTH)
+    pipe_ms_per_step = None
+    if depth >= 1:
+        from renderer_b200.dist import FramePipeline
+        do_flush = os.environ.get("B200R_BENCH_FLUSH", "1") != "0"
+
+        def flush_on(s_):
+            with torch.cuda.stream(s_):
+                flush.zero_()
+        pipe = FramePipeline(gpu, W, H, rank=rank, world=P, depth=depth, pre_frame=flush_on if do_flush else None)
+        frames = [frame_for(s_) for s_ in range(Wm + K)]         # frame state prepared outside the timed region (12 floats each)
+        for s_ in range(Wm):
+            pipe.submit(frames[s_])
+        pipe.drain()
+        barrier()
+        pipe.launches = 0
+        sampler2 = ClockSampler(local) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall0 = time.perf_counter()
+        e0.record(stream)
+        pipe.start_after(stream)
+        for i in range(K):
+            pipe.submit(frames[Wm + i])
+        pipe.join(stream)
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t_wall0
+        clocks2 = sampler2.stop() if sampler2 else None
+        pipe_total_ms = e0.elapsed_time(e1)
+        if P > 1:
+            t = torch.tensor([pipe_total_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pipe_total_ms = float(t.item())
+        pipe_ms_per_step = pipe_total_ms / K
+        launches = pipe.launches
+        if clocks2 and clocks2.get("sm_mhz"):
+            clocks = clocks2
+    ms_per_step = pipe_ms_per_step if pipe_ms_per_step is not None else serial_ms_per_step
+    total_ms = ms_per_step * K
     fps = 1000.0 / ms_per_step
     value = fps if raster else rays_total / (total_ms / 1000.0) / 1e6
 
     # ---- end-to-end through the public call with host buffers
+    e2e_depth = int(os.environ.get("B200R_E2E_DEPTH", "0")) or (2 if raster else DEFAULT_DEPTH)
+    if P == 1:
+        gpu.set_pipeline_depth(e2e_depth)
+        host_ring.extend(torch.zeros((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+                         for _ in range(e2e_depth + 1 - len(host_ring)))
+    e2e_pipe = None
+    if P > 1 and not raster:
+        from renderer_b200.dist import FramePipeline
+        e2e_pipe = FramePipeline(gpu, W, H, rank=rank, world=P, depth=e2e_depth, to_host=(rank == 0))
+        e2e_frames = [frame_for(s_) for s_ in range(Wm + K)]
+
     def time_e2e(pipelined):
+        if e2e_pipe is not None:
+            # N > 1: every rank keeps e2e_depth frames in flight; rank 0 also copies every assembled frame to page-locked host
+            # memory (on the comm stream, behind the all-gather + de-interleave of that frame)
+            for s_ in range(min(Wm, 3)):
+                e2e_pipe.submit(e2e_frames[s_])
+            e2e_pipe.drain()
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(K):
+                e2e_pipe.submit(e2e_frames[Wm + i])
+            e2e_pipe.drain()                 # every frame of the timed region is complete in rank 0's host memory
+            barrier()
+            dt = time.perf_counter() - t0
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
         for s_ in range(min(Wm, 3)):
             step_e2e(s_, pipelined)
         if P == 1:
@@ -465,9 +544,22 @@ def run_b200_arm(args, wl):
             "config": {"workload": wl["desc"], "camera": "reference -b orbit, one new frame per step",
                        "rays_per_frame": rays_total / K,
                        "raster_per_frame": ({k: tot_all[k] / K for k in ("tris_setup", "spans", "z_tests", "z_passes")} if raster else None),
-                       "l2": "flushed between timed steps (256 MiB write, outside the events)",
-                       "parallelism": "1 GPU" if P == 1 else f"row-cyclic sharding over {P} GPUs + 1 NCCL all-gather + de-interleave",
-                       "timing": "CUDA events on the launching stream, max over ranks"},
+                       "l2": ("flushed before every frame: a 256 MiB write (> 126 MB L2) enqueued on the frame's stream, INSIDE the timed region"
+                              if pipe_ms_per_step is not None and do_flush else
+                              ("NOT flushed (B200R_BENCH_FLUSH=0: experiment, not a bench value)" if pipe_ms_per_step is not None else
+                               "flushed between timed steps (256 MiB write, outside the events)")),
+                       "frames_in_flight": depth if pipe_ms_per_step is not None else 1,
+                       "parallelism": "1 GPU" if P == 1 else f"row-cyclic sharding over {P} GPUs + 1 NCCL all-gather + de-interleave per frame",
+                       "timing": ("exactly K frames between ONE start event (before the first flush) and ONE end event recorded after every "
+                                  "render/communication stream has joined the timing stream; max over ranks. Frames are independent "
+                                  "(the reference's -b orbit), so up to frames_in_flight of them overlap; `serial` below is the same K "
+                                  "frames one at a time") if pipe_ms_per_step is not None else
+                                 "CUDA events on the launching stream around every step, max over ranks"},
+            "serial": {"ms_per_step": serial_ms_per_step, "fps": 1000.0 / serial_ms_per_step,
+                       "value": (1000.0 / serial_ms_per_step) if raster else rays_total / (serial_ms_per_step * K / 1000.0) / 1e6,
+                       "gpu_launches": serial_launches,
+                       "note": "one frame at a time on one stream, L2 flushed between steps outside the per-step events; "
+                               "roofline.kernel_ms is this run's per-launch kernel time (a kernel timed alone)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic,
                          "kernel": ("rasteriser step = clears + ras_setup + ras_depth + ras_resolve (+ the 5 MLAA kernels)" if raster else
@@ -478,11 +570,15 @@ def run_b200_arm(args, wl):
             "e2e": {"value": e2e_value, "unit": unit, "fps": K / e2e_s,
                     "h2d_bytes_per_step": C.sizeof(rb.Frame), "d2h_bytes_per_step": W * H * 4,
                     "fps_blocking_call": K / e2e_sync_s,
+                    "frames_in_flight": e2e_depth,
                     "note": ("b200r_render_async + b200r_wait with page-locked host frames: frame state in, XRGB frame out, per step; "
-                             "up to 3 frames in flight (frame i copying out while frames i+1, i+2 render on two streams, the head of "
-                             "one filling the SMs the tail of the other leaves idle); every frame is complete in host memory before "
-                             "the clock stops; fps_blocking_call = one blocking b200r_render per step")
-                            if P == 1 else "frame rendered row-cyclically on all ranks, gathered, copied to rank 0's host memory, per step"},
+                             f"up to {e2e_depth + 1} frames in flight (one copying out while the next {e2e_depth} render on their own streams, "
+                             "the head of one filling the SMs the tail of another leaves idle); every frame is complete in host memory "
+                             "before the clock stops; fps_blocking_call = one blocking b200r_render per step")
+                            if P == 1 else
+                            (f"renderer_b200.dist.FramePipeline: every rank renders its rows of up to {e2e_depth} frames in flight; per frame ONE "
+                             "NCCL all-gather + de-interleave on a communication stream, then rank 0 copies the assembled frame to "
+                             "page-locked host memory; every frame is complete in rank 0's host memory before the clock stops")},
             "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall,
         }
         if per_rank:

@@ -38,6 +38,7 @@ extern "C" {
 #define B200R_BVH_STACK_SIZE 32     /* reference src/Defines.h:36 */
 #define B200R_SHADOWMAP_SIZE 1024   /* reference src/Defines.h:25 */
 #define B200R_MAX_LIGHTS     2      /* reference src/renderer.cc:277-296 (-w adds the second) */
+#define B200R_MAX_FRAMES_IN_FLIGHT 8 /* independent sets of per-frame scratch buffers (b200r_set_pipeline_depth, b200r_render_device_slot) */
 
 /* ---------------------------------------------------------------- scene records (POD)
  * These mirror the fields of the reference's Vertex / Triangle / CacheFriendlyBVHNode that the
@@ -147,21 +148,33 @@ int  b200r_download_shadowmap(b200r_ctx* ctx, int light, float* map1024x1024);
 int  b200r_render(b200r_ctx* ctx, const b200r_frame* f, uint32_t* host_xrgb);
 
 /* The same call, pipelined - for loops like main()'s benchmark loop (src/renderer.cc:491-606), where frame i+1 does
- * not depend on frame i: the call returns once the frame is ENQUEUED. Up to three frames are in flight: one being
- * copied to the host while the next two render; ray-traced frames alternate between two streams and scratch sets, so
- * the head of frame i+1 runs on the SMs that the tail of frame i (its last few long rays) leaves idle.
- * host_xrgb must stay valid, and is only complete, after b200r_wait() - or after the third following
+ * not depend on frame i: the call returns once the frame is ENQUEUED. Up to depth+1 frames are in flight (depth = 2
+ * unless b200r_set_pipeline_depth changed it): one being copied to the host while the next `depth` render; ray-traced
+ * frames rotate over `depth` streams and scratch sets, so the head of frame i+1 runs on the SMs that the tail of frame i
+ * (its last few long rays) leaves idle.
+ * host_xrgb must stay valid, and is only complete, after b200r_wait() - or after the (depth+1)-th following
  * b200r_render_async(), which reuses the slot. Page-locked caller memory is written by
  * DMA directly; pageable memory goes through an internal pinned staging buffer (copied out in b200r_wait / slot reuse).
  * b200r_render() and b200r_destroy() drain the pipeline first. */
 int  b200r_render_async(b200r_ctx* ctx, const b200r_frame* f, uint32_t* host_xrgb);
 int  b200r_wait(b200r_ctx* ctx);
+/* Frames of b200r_render_async that render concurrently: 1 (none overlap) .. B200R_MAX_FRAMES_IN_FLIGHT. Drains the
+ * pipeline first. */
+int  b200r_set_pipeline_depth(b200r_ctx* ctx, uint32_t depth);
 
 /* Same, but the frame stays in device memory (dev_xrgb is a CUDA device pointer with room for
  * rows_rendered*width words) and the work is enqueued on `cuda_stream` (a cudaStream_t, NULL = the
  * library's own stream, which is then synchronised before returning). Used by the multi-GPU path,
  * where the packed rows feed an NCCL all-gather. */
 int  b200r_render_device(b200r_ctx* ctx, const b200r_frame* f, void* dev_xrgb, void* cuda_stream);
+
+/* b200r_render_device for callers that keep several frames in flight themselves (the multi-GPU pipeline: rank r renders
+ * its rows of frame i+1 while the all-gather of frame i is on the wire): `scratch_slot` (0 .. B200R_MAX_FRAMES_IN_FLIGHT-1)
+ * selects the set of per-frame scratch buffers (job queue, merge words, hit records). Two frames may be in flight at the
+ * same time iff they use different slots; frames of the same slot must be ordered by the caller (same stream, or events).
+ * `cuda_stream` must not be NULL; nothing is synchronised. Ray-tracing modes only (the rasteriser reads a span count
+ * back per frame and has one scratch set): other modes return B200R_EINVAL. */
+int  b200r_render_device_slot(b200r_ctx* ctx, const b200r_frame* f, void* dev_xrgb, void* cuda_stream, uint32_t scratch_slot);
 
 /* Replaces: MLAA(fbi, NULL, resX, resY) (src/MLAA.h:4) applied in place on a full device frame. */
 int  b200r_mlaa_device(b200r_ctx* ctx, void* dev_xrgb, uint32_t width, uint32_t height, void* cuda_stream);

@@ -289,14 +289,26 @@ class Renderer:
 
     def render_async(self, frame, out):
         """b200r_render_async: enqueue the frame; `out` (rows x width uint32, ideally page-locked) is complete after
-        wait() or after the second following render_async()."""
-        self._pending = getattr(self, "_pending", [])[-1:] + [out]          # keep the two in-flight buffers alive
+        wait() or after the (pipeline depth + 1)-th following render_async()."""
+        self._pending = getattr(self, "_pending", [])[-getattr(self, "_depth", 2):] + [out]   # keep the in-flight buffers alive
         _check(lib().b200r_render_async(self._ctx, C.byref(frame), out.ctypes.data), self._ctx)
         return out
 
     def wait(self):
         _check(lib().b200r_wait(self._ctx), self._ctx)
         self._pending = []
+
+    def set_pipeline_depth(self, depth):
+        """b200r_set_pipeline_depth: ray-traced frames of render_async that render concurrently (1..MAX_FRAMES_IN_FLIGHT)."""
+        _check(lib().b200r_set_pipeline_depth(self._ctx, int(depth)), self._ctx)
+        self._depth = int(depth)
+        self._pending = []
+
+    def render_device_slot(self, frame, dev_ptr, stream, slot):
+        """b200r_render_device_slot: enqueue a ray-traced frame on `stream` (a cudaStream_t handle, not 0) using scratch set
+        `slot`; frames with different slots may be in flight together, nothing is synchronised."""
+        _check(lib().b200r_render_device_slot(self._ctx, C.byref(frame), C.c_void_p(dev_ptr), C.c_void_p(stream), int(slot)),
+               self._ctx)
 
     def render_device(self, frame, dev_ptr, stream=None):
         _check(lib().b200r_render_device(self._ctx, C.byref(frame), C.c_void_p(dev_ptr),

@@ -69,6 +69,8 @@ SYMBOLS = {
     "b200r_render_async": (C.c_int, [C.c_void_p, P(Frame), C.c_void_p]),
     "b200r_wait": (C.c_int, [C.c_void_p]),
     "b200r_render_device": (C.c_int, [C.c_void_p, P(Frame), C.c_void_p, C.c_void_p]),
+    "b200r_render_device_slot": (C.c_int, [C.c_void_p, P(Frame), C.c_void_p, C.c_void_p, C.c_uint32]),
+    "b200r_set_pipeline_depth": (C.c_int, [C.c_void_p, C.c_uint32]),
     "b200r_mlaa_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "b200r_deinterleave_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                             C.c_uint32, C.c_void_p]),

@@ -47,19 +47,21 @@ struct b200r_ctx {
         uint32_t* user = nullptr; size_t user_words = 0;       // where the frame finally goes
         cudaEvent_t rendered = nullptr, copied = nullptr;
         bool inflight = false, staged = false;
-    } slot[3];
-    static constexpr unsigned NSLOT = 3;       // frames in flight: one being copied out, two rendering (overlapped, see stream2)
+    } slot[B200R_MAX_FRAMES_IN_FLIGHT + 1];
+    // frames in flight of b200r_render_async: `depth` rendering (overlapped, see rstream) + one being copied out
+    unsigned depth = 2;
+    unsigned nslot() const { return depth + 1; }
     cudaStream_t copyStream = nullptr;
-    // ... and frame i+1's ray-tracing kernels run on a second stream with a second set of scratch buffers, so they fill the
-    // SMs that the tail of frame i's persistent kernel leaves idle (its last few long rays)
-    cudaStream_t stream2 = nullptr;
-    RtBuffers rt2{};
-    unsigned* d_tileCounter2 = nullptr;
+    // ... and consecutive ray-traced frames run on different streams, each with its own set of scratch buffers (rts[k],
+    // tileCounters[k]), so the head of one frame fills the SMs that the tail of the previous frame's persistent kernel
+    // leaves idle (its last few long rays). rts[0] / stream are the set every blocking call uses.
+    cudaStream_t rstream[B200R_MAX_FRAMES_IN_FLIGHT] = {};      // [0] is never created: set 0 renders on `stream`
+    RtBuffers rts[B200R_MAX_FRAMES_IN_FLIGHT] = {};
+    unsigned* tileCounters[B200R_MAX_FRAMES_IN_FLIGHT] = {};    // [0] == d_tileCounter
     unsigned asyncIdx = 0;
     unsigned* d_tileCounter = nullptr;
     DeviceCounters* d_ctr = nullptr;
     RasterBuffers rb{};
-    RtBuffers rt{};
     WireBuffers wb{};
     size_t zkey_pixels = 0;
     float4* d_attrs = nullptr; size_t attr_pixels = 0;
@@ -195,7 +197,9 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
                 prof = ctx->d_tileProf; ctx->lastTiles = nTiles;
             }
             const size_t px32 = (size_t)nTiles * 32;
-            RtBuffers& rt = scratchSet ? ctx->rt2 : ctx->rt;
+            if (scratchSet < 0 || scratchSet >= B200R_MAX_FRAMES_IN_FLIGHT) return fail(ctx, B200R_EINVAL, "scratch set out of range");
+            RtBuffers& rt = ctx->rts[scratchSet];
+            if (!ctx->tileCounters[scratchSet]) CU(cudaMalloc((void**)&ctx->tileCounters[scratchSet], 64));
             if (rt.pixels < px32) {
                 cudaFree(rt.queue); cudaFree(rt.hits); cudaFree(rt.keys); cudaFree(rt.pend);
                 rt.queue = nullptr; rt.hits = nullptr; rt.keys = nullptr; rt.pend = nullptr; rt.pixels = 0;
@@ -213,7 +217,7 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
                 CU(cudaMalloc((void**)&rt.pend, px32 * 4));
                 rt.pixels = px32;
             }
-            rt.counters = scratchSet ? ctx->d_tileCounter2 : ctx->d_tileCounter;
+            rt.counters = ctx->tileCounters[scratchSet];
             rt.forceMonolithic = getenv("B200R_MONOLITHIC_RT") != nullptr;
             rt.noPrune = getenv("B200R_NO_PRUNE") != nullptr;
             {
@@ -362,6 +366,7 @@ int b200r_init(int device, b200r_ctx** out)
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&ctx->ev0)); CU(cudaEventCreate(&ctx->ev1));
     CU(cudaMalloc((void**)&ctx->d_tileCounter, 64));
+    ctx->tileCounters[0] = ctx->d_tileCounter;
     CU(cudaMalloc((void**)&ctx->d_ctr, sizeof(DeviceCounters)));
     CU(cudaMemset(ctx->d_ctr, 0, sizeof(DeviceCounters)));
     CU(cudaMalloc((void**)&ctx->rb.spanCount, 64));
@@ -378,12 +383,13 @@ void b200r_destroy(b200r_ctx* ctx)
     for (int i = 0; i < B200R_MAX_LIGHTS; i++) cudaFree(ctx->d_shadowmap[i]);
     cudaFree(ctx->d_frame); cudaFree(ctx->d_tileCounter); cudaFree(ctx->d_ctr);
     cudaFree(ctx->wb.counts); cudaFree(ctx->wb.offsets); cudaFree(ctx->wb.blockSums); cudaFree(ctx->wb.total); cudaFree(ctx->wb.frags);
-    cudaFree(ctx->rt.queue); cudaFree(ctx->rt.hits); cudaFree(ctx->rt.keys); cudaFree(ctx->rt.pend);
-    cudaFree(ctx->rt.srays); cudaFree(ctx->rt.sword); cudaFree(ctx->rt.queue2); cudaFree(ctx->rt.warpProf); cudaFree(ctx->rt.sdon);
-    cudaFree(ctx->rt2.queue); cudaFree(ctx->rt2.hits); cudaFree(ctx->rt2.keys); cudaFree(ctx->rt2.pend);
-    cudaFree(ctx->rt2.srays); cudaFree(ctx->rt2.sword); cudaFree(ctx->rt2.queue2); cudaFree(ctx->rt2.warpProf); cudaFree(ctx->rt2.sdon);
-    cudaFree(ctx->d_tileCounter2);
-    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    for (int k = 0; k < B200R_MAX_FRAMES_IN_FLIGHT; k++) {
+        RtBuffers& rt = ctx->rts[k];
+        cudaFree(rt.queue); cudaFree(rt.hits); cudaFree(rt.keys); cudaFree(rt.pend);
+        cudaFree(rt.srays); cudaFree(rt.sword); cudaFree(rt.queue2); cudaFree(rt.warpProf); cudaFree(rt.sdon);
+        if (k) cudaFree(ctx->tileCounters[k]);
+        if (ctx->rstream[k]) cudaStreamDestroy(ctx->rstream[k]);
+    }
     cudaFree(ctx->d_attrs); cudaFree(ctx->d_mlaaScratch); cudaFree(ctx->d_mlaaLines); cudaFree(ctx->d_tileProf); cudaFree(ctx->rb.spans); cudaFree(ctx->rb.spanCount); cudaFree(ctx->rb.zkeys); cudaFree(ctx->d_shadowKeys);
     if (ctx->h_spanCount) cudaFreeHost(ctx->h_spanCount);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -592,6 +598,31 @@ int b200r_render_device(b200r_ctx* ctx, const b200r_frame* f, void* dev_xrgb, vo
     return B200R_OK;
 }
 
+int b200r_render_device_slot(b200r_ctx* ctx, const b200r_frame* f, void* dev_xrgb, void* cuda_stream, uint32_t scratch_slot)
+{
+    if (!ctx) return fail(nullptr, B200R_EINVAL, "NULL ctx");
+    if (!dev_xrgb || !cuda_stream) return fail(ctx, B200R_EINVAL, "b200r_render_device_slot needs a device frame pointer and a stream");
+    if (scratch_slot >= B200R_MAX_FRAMES_IN_FLIGHT) return fail(ctx, B200R_EINVAL, "scratch_slot out of range");
+    if (!f || !(f->mode == 0 || f->mode == B200R_MODE_RAYTRACE || f->mode == B200R_MODE_RAYTRACE_AA) || (f->flags & B200R_F_MLAA))
+        return fail(ctx, B200R_EINVAL, "b200r_render_device_slot: ray-tracing modes without MLAA only");
+    if (ctx->counting || ctx->tileProfile) return fail(ctx, B200R_ESTATE, "b200r_render_device_slot: counters / tile profile use one shared buffer; switch them off");
+    CU(cudaSetDevice(ctx->device));
+    for (auto& S : ctx->slot)
+        if (S.inflight) return fail(ctx, B200R_ESTATE, "b200r_render_device_slot while b200r_render_async frames are in flight (b200r_wait first)");
+    FrameParams fp;
+    return render_common(ctx, f, (uint32_t*)dev_xrgb, (cudaStream_t)cuda_stream, fp, (int)scratch_slot);
+}
+
+int b200r_set_pipeline_depth(b200r_ctx* ctx, uint32_t depth)
+{
+    if (!ctx) return fail(nullptr, B200R_EINVAL, "NULL ctx");
+    if (depth < 1 || depth > B200R_MAX_FRAMES_IN_FLIGHT) return fail(ctx, B200R_EINVAL, "pipeline depth must be 1..B200R_MAX_FRAMES_IN_FLIGHT");
+    int rc = b200r_wait(ctx);
+    if (rc) return rc;
+    ctx->depth = depth; ctx->asyncIdx = 0;
+    return B200R_OK;
+}
+
 namespace {
 bool host_pointer_is_pinned(const void* p)
 {
@@ -657,8 +688,8 @@ int b200r_render_async(b200r_ctx* ctx, const b200r_frame* f, uint32_t* host_xrgb
             CU(cudaEventCreateWithFlags(&S.copied, cudaEventDisableTiming));
         }
     }
-    b200r_ctx::AsyncSlot& S = ctx->slot[ctx->asyncIdx % b200r_ctx::NSLOT];
-    rc = retire_slot(ctx, S);                    // the frame submitted NSLOT calls ago: its copy must be out of S.d
+    b200r_ctx::AsyncSlot& S = ctx->slot[ctx->asyncIdx % ctx->nslot()];
+    rc = retire_slot(ctx, S);                    // the frame submitted nslot() calls ago: its copy must be out of S.d
     if (rc) return rc;
     if (S.words < words) {
         cudaFree(S.d); S.d = nullptr; S.words = 0;
@@ -672,17 +703,14 @@ int b200r_render_async(b200r_ctx* ctx, const b200r_frame* f, uint32_t* host_xrgb
         CU(cudaMallocHost((void**)&S.staging, words * 4));
         S.staging_words = words;
     }
-    // Ray-traced frames alternate between two streams / scratch sets: frame i+1 starts while the last long rays of frame i
+    // Ray-traced frames rotate over `depth` streams / scratch sets: frame i+1 starts while the last long rays of frame i
     // are still being walked (the persistent kernel's CTAs retire one by one) and takes over the SMs they free.
     // Everything else (and any profiling / counting run) stays on the one stream and is therefore serialised.
     const bool overlap = (fp.mode == B200R_MODE_RAYTRACE || fp.mode == B200R_MODE_RAYTRACE_AA) && !ctx->counting && !ctx->tileProfile &&
                          !getenv("B200R_WARP_PROFILE") && !getenv("B200R_NO_FRAME_OVERLAP") && !(f->flags & B200R_F_MLAA);
-    const int set = overlap ? (int)(ctx->asyncIdx & 1u) : 0;
-    if (set && !ctx->stream2) {
-        CU(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
-        CU(cudaMalloc((void**)&ctx->d_tileCounter2, 64));
-    }
-    cudaStream_t rs = set ? ctx->stream2 : ctx->stream;
+    const int set = overlap ? (int)(ctx->asyncIdx % ctx->depth) : 0;
+    if (set && !ctx->rstream[set]) CU(cudaStreamCreateWithFlags(&ctx->rstream[set], cudaStreamNonBlocking));
+    cudaStream_t rs = set ? ctx->rstream[set] : ctx->stream;
     rc = render_common(ctx, f, S.d, rs, fp, set);
     if (rc) return rc;
     CU(cudaEventRecord(S.rendered, rs));
@@ -698,8 +726,8 @@ int b200r_wait(b200r_ctx* ctx)
 {
     if (!ctx) return fail(nullptr, B200R_EINVAL, "NULL ctx");
     CU(cudaSetDevice(ctx->device));
-    for (unsigned k = 0; k < b200r_ctx::NSLOT; k++) {           // oldest submission first
-        int rc = retire_slot(ctx, ctx->slot[(ctx->asyncIdx + k) % b200r_ctx::NSLOT]);
+    for (unsigned k = 0; k < ctx->nslot(); k++) {               // oldest submission first
+        int rc = retire_slot(ctx, ctx->slot[(ctx->asyncIdx + k) % ctx->nslot()]);
         if (rc) return rc;
     }
     return B200R_OK;
@@ -778,12 +806,12 @@ int b200r_set_tile_profile(b200r_ctx* ctx, int enabled)
 int b200r_get_tile_profile(b200r_ctx* ctx, uint64_t* start_end_ns, uint32_t max_tiles, uint32_t* n_tiles)
 {
     if (!ctx || !n_tiles) return fail(ctx, B200R_EINVAL, "NULL argument");
-    if (ctx->rt.warpProf) {      // B200R_WARP_PROFILE: per-warp records of rt_primary_kernel (2 "tiles" per warp)
-        *n_tiles = getenv("B200R_JOB_PROFILE") ? 131072u : ctx->rt.lastPrimaryWarps * 2;     // whole buffer incl. job statistics
+    if (ctx->rts[0].warpProf) {      // B200R_WARP_PROFILE: per-warp records of rt_primary_kernel (2 "tiles" per warp)
+        *n_tiles = getenv("B200R_JOB_PROFILE") ? 131072u : ctx->rts[0].lastPrimaryWarps * 2;     // whole buffer incl. job statistics
         if (!start_end_ns) return B200R_OK;
         CU(cudaSetDevice(ctx->device));
         const uint32_t n = *n_tiles < max_tiles ? *n_tiles : max_tiles;
-        CU(cudaMemcpy(start_end_ns, ctx->rt.warpProf, (size_t)n * 16, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(start_end_ns, ctx->rts[0].warpProf, (size_t)n * 16, cudaMemcpyDeviceToHost));
         return B200R_OK;
     }
     *n_tiles = ctx->lastTiles;

@@ -227,3 +227,42 @@ def test_overlapped_async_frames_equal_blocking_frames(rb, load_scene, gpu):
         gpu.wait()
         for k in range(len(frames)):
             assert np.array_equal(outs[k], want[k]), f"rep {rep} frame {k} {specs[k]}"
+
+
+def test_frames_in_flight_on_scratch_slots_equal_blocking_frames(rb, load_scene, gpu):
+    """b200r_render_device_slot + renderer_b200.dist.FramePipeline (world 1): frames rotating over 4 streams / scratch sets,
+    and b200r_render_async at pipeline depth 4, deliver the blocking call's frames bit for bit."""
+    import numpy as np
+    import torch
+    from renderer_b200.dist import FramePipeline
+    s = load_scene("chessboard.tri")
+    gpu.upload(s)
+    W, H, n = 1280, 720, 8
+    cams = rb.Orbit.cameras(range(n))
+    frames = [rb.make_frame(rb.MODE_RAYTRACE, W, H, cams[k], flags=1 | 4, frame_index=k) for k in range(n)]
+    want = [gpu.render(f).copy() for f in frames]
+    pipe = FramePipeline(gpu, W, H, depth=4, to_host=True)
+    for base in (0, 4):
+        slots = [pipe.submit(frames[base + k]) for k in range(4)]
+        pipe.drain()
+        for k, d in enumerate(slots):
+            got = pipe.host[d].numpy().view(np.uint32)
+            assert np.array_equal(got, want[base + k]), f"pipeline frame {base + k}"
+            assert np.array_equal(pipe.full[d].cpu().numpy().view(np.uint32), want[base + k])
+    # a slot out of range / a rasteriser mode are refused, not rendered
+    import pytest
+    st = torch.cuda.Stream()
+    with pytest.raises(Exception):
+        gpu.render_device_slot(frames[0], pipe.full[0].data_ptr(), st.cuda_stream, 8)
+    with pytest.raises(Exception):
+        gpu.render_device_slot(rb.make_frame(rb.MODE_PHONG, W, H, cams[0]), pipe.full[0].data_ptr(), st.cuda_stream, 0)
+    gpu.set_pipeline_depth(4)
+    pinned = [torch.zeros((H, W), dtype=torch.int32).pin_memory() for _ in range(n)]
+    outs = [p.numpy().view(np.uint32) for p in pinned]
+    for rep in range(2):
+        for f, o in zip(frames, outs):
+            gpu.render_async(f, o)
+        gpu.wait()
+        for k in range(n):
+            assert np.array_equal(outs[k], want[k]), f"depth-4 async frame {k} rep {rep}"
+    gpu.set_pipeline_depth(2)
