@@ -44,7 +44,10 @@ WORKLOADS = {
 # Measured on one B200 (profiles/README.md, session r01i): 2 frames in flight 3620 fps, 3: 3370, 4: 3290, 6: 2990 - on one GPU a
 # third frame only adds contention; with the frame's rows dealt over N GPUs each rank's kernel is short and latency-bound, so
 # more frames are needed to fill it.
+# r01i, one GPU rendering every 2nd / 8th row only (what a rank of 2 / 8 does): 4 in flight 4940 / 15700 fps, 8 in flight 6700 (8th rows).
 DEFAULT_DEPTH = 2
+DEFAULT_DEPTH_SHARDED = 4
+FLUSH_BYTES = 144 << 20      # > 126 MB L2
 
 
 def algorithmic_bytes(c, W, rows, raster=False):
@@ -294,8 +297,8 @@ def run_b200_arm(args, wl):
     if P > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from renderer_b200.dist import init_nccl
+        dist = init_nccl(local)
 
     W, H = wl["W"], wl["H"]
     model = pyport.model_path(wl["model"])
@@ -321,7 +324,7 @@ def run_b200_arm(args, wl):
     gathered = torch.zeros((P * rows_per, W), dtype=torch.int32, device="cuda") if P > 1 else None
     full = torch.zeros((H, W), dtype=torch.int32, device="cuda")
     host = torch.zeros((H, W), dtype=torch.int32).pin_memory()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+    flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device="cuda")
 
     def step_device(step):
         """One frame, inputs resident, on torch's current stream. Returns my kernel launches."""
@@ -429,7 +432,7 @@ def run_b200_arm(args, wl):
     # frame i+1's kernels start while frame i's last long rays are still being walked, and (N > 1) the all-gather of frame i is
     # on the wire while the next frames render. The L2 flush stays: one > L2 write enqueued on the frame's stream before every
     # frame, INSIDE the timed region. One start event before the first flush, one end event after every stream has joined.
-    depth = int(os.environ.get("B200R_BENCH_DEPTH", "0")) or (0 if raster else DEFAULT_DEPTH)
+    depth = int(os.environ.get("B200R_BENCH_DEPTH", "0")) or (0 if raster else (DEFAULT_DEPTH if P == 1 else DEFAULT_DEPTH_SHARDED))
     pipe_ms_per_step = None
     if depth >= 1:
         from renderer_b200.dist import FramePipeline
@@ -440,6 +443,10 @@ def run_b200_arm(args, wl):
                 flush.zero_()
         pipe = FramePipeline(gpu, W, H, rank=rank, world=P, depth=depth, pre_frame=flush_on if do_flush else None)
         frames = [frame_for(s_) for s_ in range(Wm + K)]         # frame state prepared outside the timed region (12 floats each)
+        fake = int(os.environ.get("B200R_BENCH_FAKE_SHARD", "0"))   # developer experiment: one GPU renders rows 0, P, 2P.. only
+        if fake > 1 and P == 1:
+            for f_ in frames:
+                f_.row_first, f_.row_step = 0, fake
         for s_ in range(Wm):
             pipe.submit(frames[s_])
         pipe.drain()
@@ -452,6 +459,7 @@ def run_b200_arm(args, wl):
         pipe.start_after(stream)
         for i in range(K):
             pipe.submit(frames[Wm + i])
+        enqueue_ms_per_step = (time.perf_counter() - t_wall0) * 1000.0 / K     # host time to enqueue one frame (all its stages)
         pipe.join(stream)
         e1.record(stream)
         barrier()
@@ -472,7 +480,7 @@ def run_b200_arm(args, wl):
     value = fps if raster else rays_total / (total_ms / 1000.0) / 1e6
 
     # ---- end-to-end through the public call with host buffers
-    e2e_depth = int(os.environ.get("B200R_E2E_DEPTH", "0")) or (2 if raster else DEFAULT_DEPTH)
+    e2e_depth = int(os.environ.get("B200R_E2E_DEPTH", "0")) or (2 if raster else (DEFAULT_DEPTH if P == 1 else DEFAULT_DEPTH_SHARDED))
     if P == 1:
         gpu.set_pipeline_depth(e2e_depth)
         host_ring.extend(torch.zeros((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
@@ -544,11 +552,13 @@ def run_b200_arm(args, wl):
             "config": {"workload": wl["desc"], "camera": "reference -b orbit, one new frame per step",
                        "rays_per_frame": rays_total / K,
                        "raster_per_frame": ({k: tot_all[k] / K for k in ("tris_setup", "spans", "z_tests", "z_passes")} if raster else None),
-                       "l2": ("flushed before every frame: a 256 MiB write (> 126 MB L2) enqueued on the frame's stream, INSIDE the timed region"
+                       "l2": ("flushed before every frame: a 144 MiB write (> 126 MB L2) enqueued on the frame's stream, INSIDE the timed region"
                               if pipe_ms_per_step is not None and do_flush else
                               ("NOT flushed (B200R_BENCH_FLUSH=0: experiment, not a bench value)" if pipe_ms_per_step is not None else
-                               "flushed between timed steps (256 MiB write, outside the events)")),
+                               "flushed between timed steps (144 MiB write, outside the events)")),
                        "frames_in_flight": depth if pipe_ms_per_step is not None else 1,
+                       "host_enqueue_ms_per_step": enqueue_ms_per_step if pipe_ms_per_step is not None else None,
+                       **({"EXPERIMENT_fake_shard": fake} if pipe_ms_per_step is not None and fake > 1 else {}),
                        "parallelism": "1 GPU" if P == 1 else f"row-cyclic sharding over {P} GPUs + 1 NCCL all-gather + de-interleave per frame",
                        "timing": ("exactly K frames between ONE start event (before the first flush) and ONE end event recorded after every "
                                   "render/communication stream has joined the timing stream; max over ranks. Frames are independent "
@@ -558,7 +568,7 @@ def run_b200_arm(args, wl):
             "serial": {"ms_per_step": serial_ms_per_step, "fps": 1000.0 / serial_ms_per_step,
                        "value": (1000.0 / serial_ms_per_step) if raster else rays_total / (serial_ms_per_step * K / 1000.0) / 1e6,
                        "gpu_launches": serial_launches,
-                       "note": "one frame at a time on one stream, L2 flushed between steps outside the per-step events; "
+                       "note": "one frame at a time on one stream, L2 flushed (144 MiB write) between steps outside the per-step events; "
                                "roofline.kernel_ms is this run's per-launch kernel time (a kernel timed alone)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic,

@@ -148,6 +148,8 @@ int mlaa_on(b200r_ctx* ctx, uint32_t* d_frame, uint32_t width, uint32_t height, 
 {
     if ((width % 4) || (height % 8))
         return fail(ctx, B200R_EINVAL, "MLAA needs width % 4 == 0 and height % 8 == 0 (the reference's SSE code assumes it, MLAA.cc:396,453)");
+    if (reinterpret_cast<uintptr_t>(d_frame) & 15u)
+        return fail(ctx, B200R_EINVAL, "MLAA needs a 16-byte aligned frame (so does the reference's SSE code, MLAA.cc:453-457)");
     const size_t words = (size_t)width * height;
     if (ctx->mlaaWords < words) {
         if (ctx->d_mlaaScratch) cudaFree(ctx->d_mlaaScratch);

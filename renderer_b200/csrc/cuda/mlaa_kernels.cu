@@ -38,13 +38,22 @@ __device__ __forceinline__ unsigned mixColor(float w1, unsigned c1, float w2, un
 
 __global__ void mlaa_find_fragments_kernel(const uint32_t* __restrict__ fbi, uint32_t* __restrict__ fb0, int resX, int resY)
 {
-    const size_t n = (size_t)resX * resY;
-    for (size_t ci = (size_t)blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += (size_t)gridDim.x * blockDim.x) {
-        const int y = (int)(ci / resX), x = (int)(ci % resX);
-        const unsigned c = fbi[ci];
-        const unsigned below = (y == resY - 1) ? c : fbi[ci + resX];
-        const unsigned right = (x == resX - 1) ? c : fbi[ci + 1];
-        fb0[ci] = c | (differs(c, below) ? HF : 0u) | (differs(c, right) ? VF : 0u);
+    // four pixels per thread (resX % 4 == 0 is a precondition of the filter, MLAA.cc:453-457): 16-byte loads/stores, and
+    // no 64-bit division per pixel
+    const int qx = resX >> 2;
+    const int nq = qx * resY;
+    for (int q = (int)(blockIdx.x * blockDim.x + threadIdx.x); q < nq; q += (int)(gridDim.x * blockDim.x)) {
+        const int y = q / qx, x = (q - y * qx) << 2;
+        const size_t ci = (size_t)y * resX + x;
+        const uint4 c = *reinterpret_cast<const uint4*>(fbi + ci);
+        const uint4 b = (y == resY - 1) ? c : *reinterpret_cast<const uint4*>(fbi + ci + resX);
+        const unsigned r3 = (x + 3 == resX - 1) ? c.w : fbi[ci + 4];
+        uint4 o;
+        o.x = c.x | (differs(c.x, b.x) ? HF : 0u) | (differs(c.x, c.y) ? VF : 0u);
+        o.y = c.y | (differs(c.y, b.y) ? HF : 0u) | (differs(c.y, c.z) ? VF : 0u);
+        o.z = c.z | (differs(c.z, b.z) ? HF : 0u) | (differs(c.z, c.w) ? VF : 0u);
+        o.w = c.w | (differs(c.w, b.w) ? HF : 0u) | (differs(c.w, r3) ? VF : 0u);
+        *reinterpret_cast<uint4*>(fb0 + ci) = o;
     }
 }
 
@@ -239,42 +248,94 @@ mlaa_blend_kernel(uint32_t* fbi, const uint32_t* __restrict__ fb0, int resX, int
 // ---------------------------------------------------------------------------------------------------------
 struct __align__(16) LineRec { int ui0, ui1, li0, li1; float uh0, uh1, lh0, lh1; };      // ui1 == -2: a one-pixel line at ui0
 
+// The first pixel of a separation line (gi < sz: horizontal line at pixel gi; else vertical at pixel gi - sz): find its end,
+// its bounds and split heights, append the record to its row's (column's) list.
+__device__ __forceinline__ void line_record(const uint32_t* __restrict__ fb0, int resX, int resY, int gi, LineRec* __restrict__ recH,
+                                            LineRec* __restrict__ recV, int* __restrict__ cntH, int* __restrict__ cntV,
+                                            int* __restrict__ endH, int* __restrict__ endV, int capH, int capV)
+{
+    const int sz = resX * resY;
+    const int vertical = gi >= sz;
+    const int x = vertical ? gi - sz : gi;
+    unsigned fc; int resx, stepy, stepx, row, k;
+    if (!vertical) { fc = HF; resx = resX; stepy = resX; stepx = 1; row = x / resX; k = x - row * resX; }
+    else { fc = VF; resx = resY; stepy = 1; stepx = resX; k = x / resX; row = x - k * resX; }
+    const int yc = row * stepy;
+    int k1 = k;
+    while (k1 + 1 < resx && (fb0[yc + (k1 + 1) * stepx] & fc)) k1++;
+    atomicMax(vertical ? &endV[row] : &endH[row], k1);
+    int x0 = x; const int x1 = yc + k1 * stepx; int len = k1 - k + 1;
+    const int befor = row ? -stepy : 0, after = stepy;
+    LineRec r; r.ui0 = x0; r.ui1 = -2; r.li0 = r.li1 = -1; r.uh0 = r.uh1 = r.lh0 = r.lh1 = 0.f;
+    if (len != 1) {
+        if (x0 == yc) { x0 += stepx; len--; }
+        computeUpperBounds(r.ui0, r.ui1, r.uh0, r.uh1, fb0, fc, x0 - stepx, x1, len, stepx, befor, after, sz);
+        computeLowerBounds(r.li0, r.li1, r.lh0, r.lh1, fb0, fc, x0 - stepx, x1, len, stepx, after, sz);
+    }
+    const int slot = atomicAdd(vertical ? &cntV[row] : &cntH[row], 1);
+    if (slot < (vertical ? capV : capH)) (vertical ? recV + (size_t)row * capV : recH + (size_t)row * capH)[slot] = r;
+}
+
+// is pixel item gi (see line_record) the first pixel of a separation line of a block row?
+__device__ __forceinline__ bool is_line_start(const uint32_t* __restrict__ fb0, int resX, int resY, int gi)
+{
+    const int sz = resX * resY;
+    const int vertical = gi >= sz;
+    const int x = vertical ? gi - sz : gi;
+    const unsigned fc = vertical ? VF : HF;
+    if (!(fb0[x] & fc)) return false;                                   // 98 % of the pixels end here: no division yet
+    int row, k, stepx, resy;
+    if (!vertical) { row = x / resX; k = x - row * resX; stepx = 1; resy = resY; }
+    else { k = x / resX; row = x - k * resX; stepx = resX; resy = resX; }
+    if (row >= resy - 1) return false;                                  // the last row / column is never a block row (MLAA.cc:556-557)
+    if (k > 0 && (fb0[x - stepx] & fc)) return false;                   // not the first pixel of its run
+    return true;
+}
+
+// one pass over both orientations; the thread that finds a line start also walks it (B200R_MLAA_FULLSCAN: kept for A/B)
 __global__ void __launch_bounds__(256)
 mlaa_lines_kernel(const uint32_t* __restrict__ fb0, int resX, int resY, LineRec* __restrict__ recH, LineRec* __restrict__ recV,
                   int* __restrict__ cntH, int* __restrict__ cntV, int* __restrict__ endH, int* __restrict__ endV, int capH, int capV)
 {
-    const int sz = resX * resY;
-    const int total = 2 * sz;
-    for (int gi = (int)(blockIdx.x * blockDim.x + threadIdx.x); gi < total; gi += (int)(gridDim.x * blockDim.x)) {
-        const int vertical = gi >= sz;
-        const int x = vertical ? gi - sz : gi;
-        unsigned fc; int resx, resy, stepy, stepx, row, k;
-        if (!vertical) { fc = HF; resx = resX; resy = resY; stepy = resX; stepx = 1; row = x / resX; k = x - row * resX; }
-        else { fc = VF; resx = resY; resy = resX; stepy = 1; stepx = resX; k = x / resX; row = x - k * resX; }
-        if (row >= resy - 1) continue;                                  // the last row / column is never a block row (MLAA.cc:556-557)
-        if (!(fb0[x] & fc)) continue;
-        if (k > 0 && (fb0[x - stepx] & fc)) continue;                   // not the first pixel of its run
-        const int yc = row * stepy;
-        int k1 = k;
-        while (k1 + 1 < resx && (fb0[yc + (k1 + 1) * stepx] & fc)) k1++;
-        atomicMax(vertical ? &endV[row] : &endH[row], k1);
-        int x0 = x; const int x1 = yc + k1 * stepx; int len = k1 - k + 1;
-        const int befor = row ? -stepy : 0, after = stepy;
-        LineRec r; r.ui0 = x0; r.ui1 = -2; r.li0 = r.li1 = -1; r.uh0 = r.uh1 = r.lh0 = r.lh1 = 0.f;
-        if (len != 1) {
-            if (x0 == yc) { x0 += stepx; len--; }
-            computeUpperBounds(r.ui0, r.ui1, r.uh0, r.uh1, fb0, fc, x0 - stepx, x1, len, stepx, befor, after, sz);
-            computeLowerBounds(r.li0, r.li1, r.lh0, r.lh1, fb0, fc, x0 - stepx, x1, len, stepx, after, sz);
-        }
-        const int slot = atomicAdd(vertical ? &cntV[row] : &cntH[row], 1);
-        if (slot < (vertical ? capV : capH)) (vertical ? recV + (size_t)row * capV : recH + (size_t)row * capH)[slot] = r;
-    }
+    const int total = 2 * resX * resY;
+    for (int gi = (int)(blockIdx.x * blockDim.x + threadIdx.x); gi < total; gi += (int)(gridDim.x * blockDim.x))
+        if (is_line_start(fb0, resX, resY, gi)) line_record(fb0, resX, resY, gi, recH, recV, cntH, cntV, endH, endV, capH, capV);
 }
 
-__global__ void mlaa_lines_reset_kernel(int* __restrict__ cnt, int* __restrict__ lastEnd, int n)
+// default: the scan only LISTS the line starts (warp-aggregated append) ...
+__global__ void __launch_bounds__(256)
+mlaa_line_starts_kernel(const uint32_t* __restrict__ fb0, int resX, int resY, int* __restrict__ list, int* __restrict__ listCount)
+{
+    const int total = 2 * resX * resY;
+    const unsigned lane = threadIdx.x & 31u;
+    const int stride = (int)(gridDim.x * blockDim.x);
+    for (int g0 = (int)(blockIdx.x * blockDim.x + threadIdx.x) - (int)lane; g0 < total; g0 += stride) {    // warp-uniform trip count
+        const int gi = g0 + (int)lane;
+        const bool start = gi < total && is_line_start(fb0, resX, resY, gi);
+        const unsigned m = __ballot_sync(0xffffffffu, start);
+        if (!m) continue;
+        int base = 0;
+        if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(listCount, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (start) list[base + __popc(m & ((1u << lane) - 1u))] = gi;
+    }
+}
+// ... and the walks along the lines run one line per thread, every lane busy
+__global__ void __launch_bounds__(128)
+mlaa_line_records_kernel(const uint32_t* __restrict__ fb0, int resX, int resY, const int* __restrict__ list, const int* __restrict__ listCount,
+                         LineRec* __restrict__ recH, LineRec* __restrict__ recV, int* __restrict__ cntH, int* __restrict__ cntV,
+                         int* __restrict__ endH, int* __restrict__ endV, int capH, int capV)
+{
+    const int n = *listCount;
+    for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < n; i += (int)(gridDim.x * blockDim.x))
+        line_record(fb0, resX, resY, list[i], recH, recV, cntH, cntV, endH, endV, capH, capV);
+}
+
+__global__ void mlaa_lines_reset_kernel(int* __restrict__ cnt, int* __restrict__ lastEnd, int n, int* __restrict__ listCount)
 {
     const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (i < n) { cnt[i] = 0; lastEnd[i] = -1; }
+    if (i == 0) *listCount = 0;
 }
 
 // The ordered part: one CTA per 8-row (8-column) block of the given parity, rows in order, one thread per line record.
@@ -329,7 +390,10 @@ mlaa_blend_lines_kernel(uint32_t* fbi, const uint32_t* __restrict__ fb0, int res
 size_t mlaa_lines_bytes(int resX, int resY)
 {
     const size_t capH = (size_t)resX / 2 + 1, capV = (size_t)resY / 2 + 1;
-    return ((size_t)resY * capH + (size_t)resX * capV) * sizeof(LineRec) + 2 * ((size_t)resX + resY) * sizeof(int);
+    // records per row / column, their counts and right-most ends, then the list of line starts (every line covers >= 1 flagged
+    // pixel of its orientation: at most resX*resY starts in all... per orientation at most half the pixels) + its counter
+    return ((size_t)resY * capH + (size_t)resX * capV) * sizeof(LineRec) + 2 * ((size_t)resX + resY) * sizeof(int) +
+           ((size_t)resX * resY + 2 * ((size_t)resX + resY) + 4) * sizeof(int);
 }
 
 cudaError_t launch_mlaa(uint32_t* d_frame, uint32_t* d_scratch, int resX, int resY, int numSMs, cudaStream_t st, int& launches,
@@ -347,8 +411,15 @@ cudaError_t launch_mlaa(uint32_t* d_frame, uint32_t* d_scratch, int resX, int re
         LineRec* recV = recH + (size_t)resY * capH;
         int* cntH = reinterpret_cast<int*>(recV + (size_t)resX * capV);
         int* cntV = cntH + resY; int* endH = cntV + resX; int* endV = endH + resY;
-        mlaa_lines_reset_kernel<<<(resX + resY + 255) / 256, 256, 0, st>>>(cntH, endH, resX + resY);   // cntH|cntV and endH|endV are contiguous
-        mlaa_lines_kernel<<<numSMs * 8, 256, 0, st>>>(d_scratch, resX, resY, recH, recV, cntH, cntV, endH, endV, capH, capV);
+        int* listCount = endV + resX; int* list = listCount + 4;
+        mlaa_lines_reset_kernel<<<(resX + resY + 255) / 256, 256, 0, st>>>(cntH, endH, resX + resY, listCount);   // cntH|cntV and endH|endV are contiguous
+        const bool fullScan = getenv("B200R_MLAA_FULLSCAN") != nullptr;
+        if (fullScan) mlaa_lines_kernel<<<numSMs * 8, 256, 0, st>>>(d_scratch, resX, resY, recH, recV, cntH, cntV, endH, endV, capH, capV);
+        else {
+            mlaa_line_starts_kernel<<<numSMs * 8, 256, 0, st>>>(d_scratch, resX, resY, list, listCount);
+            mlaa_line_records_kernel<<<numSMs * 8, 128, 0, st>>>(d_scratch, resX, resY, list, listCount, recH, recV, cntH, cntV, endH, endV, capH, capV);
+            launches += 1;
+        }
         if (h0 > 0) mlaa_blend_lines_kernel<<<h0, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 0, 0, recH, cntH, endH, capH);
         if (h1 > 0) mlaa_blend_lines_kernel<<<h1, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 0, 1, recH, cntH, endH, capH);
         if (v0 > 0) mlaa_blend_lines_kernel<<<v0, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 1, 0, recV, cntV, endV, capV);

@@ -61,8 +61,8 @@ class FramePipeline:
     (b200r_render_device_slot), a packed shard, the all-gathered shards and the assembled frame. Stage order per frame:
 
         render stream d : [wait: slot d's previous frame has left its buffers] -> this rank's rows of frame i
-        comm stream     : [wait: rendered] -> ONE all-gather of the packed rows (NCCL) -> de-interleave -> (optional, the
-                          `to_host` rank) copy of the assembled frame to page-locked host memory
+        comm stream     : [wait: rendered] -> ONE all-gather of the packed rows (NCCL) -> de-interleave
+        copy stream     : (optional, the `to_host` rank) [wait: assembled] -> the frame to page-locked host memory
 
     so the all-gather of frame i is on the wire while frames i+1 .. i+depth-1 render, and the head of each frame's
     persistent kernel fills the SMs that the tail of the previous frame (its last few long rays) leaves idle.
@@ -80,9 +80,13 @@ class FramePipeline:
         dev = torch.device("cuda", torch.cuda.current_device())
         i32 = dict(dtype=torch.int32, device=dev)
         self.render_streams = [torch.cuda.Stream() for _ in range(depth)]
-        self.comm = torch.cuda.Stream()
+        # high priority: when a render CTA retires, the pending all-gather / de-interleave CTAs get its SM before the next
+        # frame's persistent CTAs do (those would hold it for a whole frame)
+        self.comm = torch.cuda.Stream(priority=-1)
         self.rendered = [torch.cuda.Event() for _ in range(depth)]
         self.free = [torch.cuda.Event() for _ in range(depth)]
+        self.assembled = [torch.cuda.Event() for _ in range(depth)]
+        self.copy = torch.cuda.Stream()
         self.full = [torch.zeros((height, width), **i32) for _ in range(depth)]
         if world > 1:
             self.shard = [torch.zeros((self.rps, width), **i32) for _ in range(depth)]
@@ -120,9 +124,14 @@ class FramePipeline:
                     self.gpu.deinterleave_device(self.gathered[d].data_ptr(), self.full[d].data_ptr(), self.W, self.H,
                                                  self.P, self.comm.cuda_stream)
                     self.launches += 1
-                if self.host is not None:
+            if self.host is not None:                   # copy-out on its own stream: the next frame's all-gather does not wait for it
+                self.assembled[d].record(self.comm)
+                self.copy.wait_event(self.assembled[d])
+                with torch.cuda.stream(self.copy):
                     self.host[d].copy_(self.full[d], non_blocking=True)
-            self.free[d].record(self.comm)
+                self.free[d].record(self.copy)
+            else:
+                self.free[d].record(self.comm)
         else:
             self.free[d].record(rs)
         self.submitted += 1
@@ -133,14 +142,31 @@ class FramePipeline:
         for s in self.render_streams:
             stream.wait_stream(s)
         stream.wait_stream(self.comm)
+        stream.wait_stream(self.copy)
 
     def start_after(self, stream):
         """Nothing submitted from now on starts before `stream`'s current tail (e.g. the start event of a timed region)."""
         for s in self.render_streams:
             s.wait_stream(stream)
         self.comm.wait_stream(stream)
+        self.copy.wait_stream(stream)
 
     def drain(self):
         for s in self.render_streams:
             s.synchronize()
         self.comm.synchronize()
+        self.copy.synchronize()
+
+
+def init_nccl(local_rank):
+    """torch.distributed over NCCL with the communicator's internal stream at high priority (see FramePipeline.comm)."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", local_rank)
+    try:
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+    except (AttributeError, TypeError):
+        dist.init_process_group("nccl", device_id=dev)
+    return dist

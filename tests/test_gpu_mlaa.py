@@ -36,6 +36,10 @@ def test_mlaa_vs_oracle(rb, pyport, load_scene, gpu, monkeypatch, model, mode, s
     scan = gpu.render(f)                                 # row-scanning kernels: lines found inside the ordered loop
     monkeypatch.delenv("B200R_MLAA_SCAN")
     assert np.array_equal(got, scan)
+    monkeypatch.setenv("B200R_MLAA_FULLSCAN", "1")
+    full = gpu.render(f)                                 # two-stage, but the scanning thread also walks the line it finds
+    monkeypatch.delenv("B200R_MLAA_FULLSCAN")
+    assert np.array_equal(got, full)
     plain = gpu.render(rb.make_frame(mode, size[0], size[1], cam))
     assert 0 < int((plain != got).sum()) < 0.2 * got.size       # the filter touches edges only
 

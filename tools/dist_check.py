@@ -23,7 +23,8 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     os.environ.setdefault("NCCL_DEBUG", "WARN")
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from renderer_b200.dist import init_nccl
+    init_nccl(local)
     model = pyport.model_path("chessboard.tri")
     scene = rb.Scene(model).UpdateBoundingVolumeHierarchy(model + ".bvh")
     gpu = rb.Renderer(local)
