@@ -47,7 +47,7 @@ static void usage()
                     "       9 : raytracing, with shadows and reflections\n"
                     "       0 : raytracing, with shadows, reflections and anti-aliasing\n"
                     "  --width W --height H --no-reflections --no-shadows --ao N --mlaa\n"
-                    "  --dump PREFIX --frames a,b,c --device D --host-bvh\n");
+                    "  --dump PREFIX --frames a,b,c --device D --host-bvh --frames-in-flight N (1..8, default 2)\n");
     exit(0);
 }
 
@@ -64,6 +64,7 @@ int main(int argc, char* argv[])
     unsigned benchmarkFrames = 100;
     unsigned W = 800, H = 600, flags = B200R_F_DEFAULT, ao = 0;
     int device = 0;
+    unsigned inFlight = 2;               // ray-traced frames rendering concurrently (b200r_set_pipeline_depth)
     bool hostBvh = false;
     std::string dumpPrefix;
     std::set<unsigned> dumpFrames;
@@ -72,7 +73,8 @@ int main(int argc, char* argv[])
                                 {"no-reflections", no_argument, 0, 1002}, {"no-shadows", no_argument, 0, 1003},
                                 {"ao", required_argument, 0, 1004}, {"mlaa", no_argument, 0, 1005},
                                 {"dump", required_argument, 0, 1006}, {"frames", required_argument, 0, 1007},
-                                {"device", required_argument, 0, 1008}, {"host-bvh", no_argument, 0, 1009}, {0, 0, 0, 0}};
+                                {"device", required_argument, 0, 1008}, {"host-bvh", no_argument, 0, 1009},
+                                {"frames-in-flight", required_argument, 0, 1010}, {0, 0, 0, 0}};
     int c;
     opterr = 0;
     while ((c = getopt_long(argc, argv, "hbrwn:m:", longopts, nullptr)) != -1) switch (c) {
@@ -95,6 +97,7 @@ int main(int argc, char* argv[])
         case 1007: { char* p = optarg; while (*p) { dumpFrames.insert((unsigned)strtoul(p, &p, 10)); if (*p == ',') p++; else break; } } break;
         case 1008: device = atoi(optarg); break;
         case 1009: hostBvh = true; break;
+        case 1010: inFlight = (unsigned)atoi(optarg); if (inFlight < 1 || inFlight > B200R_MAX_FRAMES_IN_FLIGHT) usage(); break;
         case '?': fprintf(stderr, "No such option (%c)\n", (char)optopt); usage(); break;
         default: break;
     }
@@ -133,8 +136,10 @@ int main(int argc, char* argv[])
     }
 
     // Frames of the orbit do not depend on each other, so the loop is pipelined: b200r_render_async returns when frame i is
-    // enqueued, its copy-out and its tail overlap the following frames (three host frames rotate). Dumped frames use the blocking call.
-    std::vector<uint32_t> fb[3] = {std::vector<uint32_t>((size_t)W * H), std::vector<uint32_t>((size_t)W * H), std::vector<uint32_t>((size_t)W * H)};
+    // enqueued, its copy-out and its tail overlap the following frames (inFlight + 1 host frames rotate). Dumped frames use the
+    // blocking call.
+    if (b200r_set_pipeline_depth(ctx, inFlight)) { fprintf(stderr, "%s\n", b200r_last_error(ctx)); return 1; }
+    std::vector<std::vector<uint32_t>> fb(inFlight + 1, std::vector<uint32_t>((size_t)W * H));
     b200r_orbit orbit; b200r_orbit_init(&orbit);
     unsigned framesDrawn = 0;
     double msSpentDrawing = 0, lastReport = now_ms();
@@ -146,7 +151,7 @@ int main(int argc, char* argv[])
         b200r_frame_defaults(&f, mode, W, H, eye, mv, nLights);
         f.flags = flags; if (ao) f.ao_samples = ao; f.frame_index = framesDrawn;
         const bool dump = !dumpPrefix.empty() && (dumpFrames.empty() || dumpFrames.count(framesDrawn));
-        std::vector<uint32_t>& out = fb[framesDrawn % 3u];
+        std::vector<uint32_t>& out = fb[framesDrawn % (inFlight + 1)];
         const double t0 = now_ms();
         const int rc = dump ? b200r_render(ctx, &f, out.data()) : b200r_render_async(ctx, &f, out.data());
         if (rc) { fprintf(stderr, "%s\n", b200r_last_error(ctx)); return 1; }
