@@ -195,6 +195,11 @@ int  b200r_build_bvh(b200r_ctx* ctx, const b200r_vertex* verts, uint32_t n_verts
 int  b200r_selftest_bvh_steps_host(const b200r_vertex* verts, uint32_t n_verts, const b200r_tri* tris, uint32_t n_tris,
                                    b200r_bvhnode* nodes_out, uint32_t nodes_cap, int32_t* tri_idx_out,
                                    uint32_t* n_nodes, int32_t* depth);
+/* Test hook (no device needed): the MLAA step functions the device kernels are made of (csrc/mlaa_steps.h: flags, line
+ * bounds, split heights, in-place blends - `batched` != 0: with the 8-pixel batched loads the device uses) run in plain
+ * loops on the host, in place on a width x height frame. Not a rendering path. */
+int  b200r_selftest_mlaa_steps_host(uint32_t* frame_xrgb, uint32_t width, uint32_t height, int batched);
+
 
 /* Numerics self-test: the slab test's shared-reciprocal divide (DESIGN.md "division") against the compiler's IEEE
  * divide on `samples` random operand pairs drawn from the whole domain in which the fast path is used.

@@ -13,28 +13,15 @@
 // Float maths as in the reference (mixColor's float products + x86 byte truncation), -fmad=false.
 #include "device_types.cuh"
 #include "rt_kernels.cuh"
+#include "../mlaa_steps.h"
 
 namespace b200r {
 namespace {
 
-constexpr unsigned HF = 1u << 31, VF = 1u << 30;
+constexpr unsigned HF = MLAA_HF, VF = MLAA_VF;
+constexpr int BLEND_BATCH = 8;            // pixels of a blend run loaded together (mlaa_steps.h, mlaa_blendRun)
 
-// ssedif (MLAA.cc:47-55): some byte differs by >= 16
-__device__ __forceinline__ bool differs(unsigned a, unsigned b)
-{
-    const unsigned d = __vabsdiffu4(a, b);
-    return (d & 0xF0F0F0F0u) != 0;
-}
-
-__device__ __forceinline__ int sumColor(unsigned c) { return (int)((c >> 16) & 0xff) + (int)((c >> 8) & 0xff) + (int)(c & 0xff); }
-
-__device__ __forceinline__ unsigned mixColor(float w1, unsigned c1, float w2, unsigned c2)
-{
-    const float r1 = (float)((c1 >> 16) & 0xff), g1 = (float)((c1 >> 8) & 0xff), b1 = (float)(c1 & 0xff);
-    const float r2 = (float)((c2 >> 16) & 0xff), g2 = (float)((c2 >> 8) & 0xff), b2 = (float)(c2 & 0xff);
-    const unsigned r = u8_x86(r1 * w1 + r2 * w2), g = u8_x86(g1 * w1 + g2 * w2), b = u8_x86(b1 * w1 + b2 * w2);
-    return (r << 16) | (g << 8) | b;
-}
+__device__ __forceinline__ bool differs(unsigned a, unsigned b) { return mlaa_differs(a, b); }
 
 __global__ void mlaa_find_fragments_kernel(const uint32_t* __restrict__ fbi, uint32_t* __restrict__ fb0, int resX, int resY)
 {
@@ -57,139 +44,18 @@ __global__ void mlaa_find_fragments_kernel(const uint32_t* __restrict__ fbi, uin
     }
 }
 
-__device__ __forceinline__ float getSplitHeight(const uint32_t* __restrict__ fb, int l, int icb, int icm, int ipb, int ipm)
-{
-    const int cc = sumColor(fb[icb]), cu = sumColor(fb[icm]), pc = sumColor(fb[ipb]), pu = sumColor(fb[ipm]);
-    return (float)(l * (pc - cu) + (cc - cu) - (pc - pu)) / (float)(l * ((cc - cu) + (pc - pu)) + (cc - cu) - (pc - pu));
-}
-
-__device__ void computeUpperBounds(int& s0, int& s1, float& h0, float& h1, const uint32_t* __restrict__ fb0, unsigned fc,
-                                   int x0, int x1, int len, int stepx, int befor, int after, int sz)
-{
-    s0 = s1 = -1;
-    int nsteps = 0, xi = x0, t0 = -1, t1 = -1;
-    const unsigned fo = fc ^ (HF | VF);
-    do {
-        if ((fb0[xi] & fo) && (fb0[xi + befor] & fc)) {
-            h0 = getSplitHeight(fb0, len - nsteps, xi + stepx, xi + stepx + after, xi + befor, xi);
-            if (0.f < h0 && h0 < 1.f) { s0 = xi + stepx; break; }
-        }
-        if ((fb0[xi] & fo) && t0 == -1) t0 = xi;
-        xi += stepx;
-        nsteps++;
-    } while (xi < x1);
-    if (s0 == -1 && t0 != -1) { h0 = 0.5f; s0 = t0 + stepx; }
-    if (x1 + stepx >= sz) { if (fb0[x1] & fo) t1 = x1; x1 -= stepx; }
-    xi = x1;
-    do {
-        if ((fb0[xi] & fo) && (fb0[xi + stepx + befor] & fc)) {
-            h1 = getSplitHeight(fb0, nsteps, xi + stepx, xi + stepx + befor, xi + after, xi);
-            if (0.f < h1 && h1 < 1.f) { s1 = xi; break; }
-        }
-        if ((fb0[xi] & fo) && t1 == -1) t1 = xi;
-        xi -= stepx;
-        nsteps++;
-    } while (xi > x0);
-    if (s1 == -1 && t1 != -1) { h1 = 0.5f; s1 = t1; }
-}
-
-__device__ void computeLowerBounds(int& s0, int& s1, float& h0, float& h1, const uint32_t* __restrict__ fb0, unsigned fc,
-                                   int x0, int x1, int len, int stepx, int after, int sz)
-{
-    s0 = s1 = -1;
-    int nsteps = 0, xi = x0, t0 = -1, t1 = -1;
-    const unsigned fo = fc ^ (HF | VF);
-    do {
-        const int xia = xi + after;
-        if ((fb0[xia] & fo) && (fb0[xia] & fc)) {
-            if (xia + after < sz) h0 = getSplitHeight(fb0, len - nsteps, xia + stepx, xi + stepx, xia + after, xia);
-            else h0 = 0.5f;
-            if (0.f < h0 && h0 < 1.f) { s0 = xi + stepx; break; }
-        }
-        if ((fb0[xia] & fo) && t0 == -1) t0 = xi;
-        xi += stepx;
-        nsteps++;
-    } while (xi < x1);
-    if (s0 == -1 && t0 != -1) { h0 = 0.5f; s0 = t0 + stepx; }
-    if (x1 + stepx >= sz) { if (fb0[x1] & fo) t1 = x1; x1 -= stepx; }
-    xi = x1;
-    do {
-        const int xia = xi + after;
-        if ((fb0[xia] & fo) && (fb0[xia + stepx] & fo)) {
-            if (xia + after < sz) h1 = getSplitHeight(fb0, nsteps, xia + stepx, xia + after + stepx, xi, xia);
-            else h1 = 0.5f;
-            if (0.f < h1 && h1 < 1.f) { s1 = xi; break; }
-        }
-        if ((fb0[xia] & fo) && t1 == -1) t1 = xi;
-        xi -= stepx;
-        nsteps++;
-    } while (xi > x0);
-    if (s1 == -1 && t1 != -1) { h1 = 0.5f; s1 = t1; }
-}
-
-__device__ void blendInterval(uint32_t* fbi, int x0, int x1, float h0, float h1, int stepx, int other, bool ushape)
-{
-    float dh0 = ((2.f * (1.f - h0)) * (float)stepx) / (float)(x1 - x0 + stepx);
-    float dh1 = ((2.f * (1.f - h1)) * (float)stepx) / (float)(x1 - x0 + stepx);
-    int shift = other < 0 ? -other : 0;
-    x0 += shift; x1 += shift;
-    const int middle = (x0 + x1) / 2;
-    float area = h0 + 0.5f * dh0;
-    if (h0 == 0.f) {
-        x0 += 1 + (x1 - x0) / stepx;
-        area = dh1;
-    } else {
-        do {
-            fbi[x0] = mixColor(area, fbi[x0], 1.f - area, fbi[x0 + other]);
-            area += dh0;
-            x0 += stepx;
-        } while (x0 < middle);
-        if (x0 == middle) {
-            fbi[x0] = mixColor((1.f - dh0 / 8.f), fbi[x0], dh0 / 8.f, fbi[x0 + other]);
-            if (!ushape) fbi[x0 + other] = mixColor(dh1 / 8.f, fbi[x0], (1.f - dh1 / 8.f), fbi[x0 + other]);
-            x0 += stepx;
-            area = dh1;
-        } else {
-            area = 0.5f * dh1;
-        }
-    }
-    if (h1 == 0.f) return;
-    if (ushape) { area = 1.f - area; dh1 = -dh1; }
-    shift = ushape ? 0 : other;
-    do {
-        fbi[x0 + shift] = mixColor(area, fbi[x0], 1.f - area, fbi[x0 + other]);
-        area += dh1;
-        x0 += stepx;
-    } while (x0 <= x1);
-}
-
-__device__ __forceinline__ void blend_one_cell(uint32_t* fbi, int x0, int after)
-{
-    const float weightc = 7.0f / 8;
-    fbi[x0] = mixColor(weightc, fbi[x0], 1.f - weightc, fbi[x0 + after]);
-    fbi[x0 + after] = mixColor(1.f - weightc, fbi[x0], weightc, fbi[x0 + after]);
-}
-
 // One separation line [x0, x1] of row/column yc (the body of the while loop at MLAA.cc:565-699)
+template <int BATCH>
 __device__ void process_line(uint32_t* fbi, const uint32_t* __restrict__ fb0, unsigned fc, int yc, int x0, int x1, int len,
                              int stepx, int befor, int after, int sz)
 {
-    if (len == 1) { blend_one_cell(fbi, x0, after); return; }
-    if (x0 == yc) { x0 += stepx; len--; }
-    int ui0, ui1, li0, li1; float uh0 = 0.f, uh1 = 0.f, lh0 = 0.f, lh1 = 0.f;
-    computeUpperBounds(ui0, ui1, uh0, uh1, fb0, fc, x0 - stepx, x1, len, stepx, befor, after, sz);
-    computeLowerBounds(li0, li1, lh0, lh1, fb0, fc, x0 - stepx, x1, len, stepx, after, sz);
-    bool done = false;
-    if (ui0 != -1 && li1 != -1 && ui0 < li1) { blendInterval(fbi, ui0, li1, uh0, lh1, stepx, after, false); done = true; }
-    if (li0 != -1 && ui1 != -1 && li0 < ui1) { blendInterval(fbi, li0, ui1, lh0, uh1, stepx, befor, false); done = true; }
-    if (!done) {
-        if (ui0 != -1 && ui1 != -1 && ui0 < ui1) blendInterval(fbi, ui0, ui1, uh0, uh1, stepx, after, true);
-        if (li0 != -1 && li1 != -1 && li0 < li1) blendInterval(fbi, li0, li1, lh0, lh1, stepx, befor, true);
-    }
+    const MlaaLineRec r = mlaa_line_bounds<BATCH>(fb0, fc, yc, x0, x1, len, stepx, befor, after, sz);
+    mlaa_line_blend<BATCH>(fbi, r, stepx, befor, after);
 }
 
 // One blending job = one 8-row (vertical == 0) or 8-column (vertical == 1) block; one CTA per job.
 // `yodd` selects the parity half of the reference's job list (MLAA.cc:545-552).
+template <int BATCH>
 __global__ void __launch_bounds__(256)
 mlaa_blend_kernel(uint32_t* fbi, const uint32_t* __restrict__ fb0, int resX, int resY, int vertical, int yodd)
 {
@@ -217,7 +83,7 @@ mlaa_blend_kernel(uint32_t* fbi, const uint32_t* __restrict__ fb0, int resX, int
             int k1 = k;
             while (k1 + 1 < resx && (fb0[yc + (k1 + 1) * stepx] & fc)) k1++;
             atomicMax(&s_lastEnd, k1);
-            process_line(fbi, fb0, fc, yc, x, yc + k1 * stepx, k1 - k + 1, stepx, befor, after, sz);
+            process_line<BATCH>(fbi, fb0, fc, yc, x, yc + k1 * stepx, k1 - k + 1, stepx, befor, after, sz);
         }
         __syncthreads();
         // The SSE scan quirk of the horizontal search (see oracle/port/mlaa_port.cpp): when the last line of the row
@@ -229,7 +95,7 @@ mlaa_blend_kernel(uint32_t* fbi, const uint32_t* __restrict__ fb0, int resX, int
                 const int base = yc + resx;                       // first pixel of the next row
                 for (int q = 0; q < 4; q++)
                     if (fb0[base + q] & HF) {
-                        if (base + q + after < sz) blend_one_cell(fbi, base + q, after);   // (the reference would write out of bounds)
+                        if (base + q + after < sz) mlaa_blend_one_cell(fbi, base + q, after);   // (the reference would write out of bounds)
                         break;
                     }
             }
@@ -246,10 +112,11 @@ mlaa_blend_kernel(uint32_t* fbi, const uint32_t* __restrict__ fb0, int resX, int
 // the in-place blends of the rows' records: no scan over the 98 % of pixels that carry no flag, and no serial walks
 // along the lines inside the ordered loop (4K frame: 4 x mlaa_blend_kernel = 1.07 ms of a 1.19 ms frame before).
 // ---------------------------------------------------------------------------------------------------------
-struct __align__(16) LineRec { int ui0, ui1, li0, li1; float uh0, uh1, lh0, lh1; };      // ui1 == -2: a one-pixel line at ui0
+using LineRec = MlaaLineRec;
 
 // The first pixel of a separation line (gi < sz: horizontal line at pixel gi; else vertical at pixel gi - sz): find its end,
 // its bounds and split heights, append the record to its row's (column's) list.
+template <int BATCH>
 __device__ __forceinline__ void line_record(const uint32_t* __restrict__ fb0, int resX, int resY, int gi, LineRec* __restrict__ recH,
                                             LineRec* __restrict__ recV, int* __restrict__ cntH, int* __restrict__ cntV,
                                             int* __restrict__ endH, int* __restrict__ endV, int capH, int capV)
@@ -264,14 +131,8 @@ __device__ __forceinline__ void line_record(const uint32_t* __restrict__ fb0, in
     int k1 = k;
     while (k1 + 1 < resx && (fb0[yc + (k1 + 1) * stepx] & fc)) k1++;
     atomicMax(vertical ? &endV[row] : &endH[row], k1);
-    int x0 = x; const int x1 = yc + k1 * stepx; int len = k1 - k + 1;
     const int befor = row ? -stepy : 0, after = stepy;
-    LineRec r; r.ui0 = x0; r.ui1 = -2; r.li0 = r.li1 = -1; r.uh0 = r.uh1 = r.lh0 = r.lh1 = 0.f;
-    if (len != 1) {
-        if (x0 == yc) { x0 += stepx; len--; }
-        computeUpperBounds(r.ui0, r.ui1, r.uh0, r.uh1, fb0, fc, x0 - stepx, x1, len, stepx, befor, after, sz);
-        computeLowerBounds(r.li0, r.li1, r.lh0, r.lh1, fb0, fc, x0 - stepx, x1, len, stepx, after, sz);
-    }
+    const LineRec r = mlaa_line_bounds<BATCH>(fb0, fc, yc, x, yc + k1 * stepx, k1 - k + 1, stepx, befor, after, sz);
     const int slot = atomicAdd(vertical ? &cntV[row] : &cntH[row], 1);
     if (slot < (vertical ? capV : capH)) (vertical ? recV + (size_t)row * capV : recH + (size_t)row * capH)[slot] = r;
 }
@@ -299,7 +160,7 @@ mlaa_lines_kernel(const uint32_t* __restrict__ fb0, int resX, int resY, LineRec*
 {
     const int total = 2 * resX * resY;
     for (int gi = (int)(blockIdx.x * blockDim.x + threadIdx.x); gi < total; gi += (int)(gridDim.x * blockDim.x))
-        if (is_line_start(fb0, resX, resY, gi)) line_record(fb0, resX, resY, gi, recH, recV, cntH, cntV, endH, endV, capH, capV);
+        if (is_line_start(fb0, resX, resY, gi)) line_record<1>(fb0, resX, resY, gi, recH, recV, cntH, cntV, endH, endV, capH, capV);
 }
 
 // default: the scan only LISTS the line starts (warp-aggregated append) ...
@@ -321,6 +182,7 @@ mlaa_line_starts_kernel(const uint32_t* __restrict__ fb0, int resX, int resY, in
     }
 }
 // ... and the walks along the lines run one line per thread, every lane busy
+template <int BATCH>
 __global__ void __launch_bounds__(128)
 mlaa_line_records_kernel(const uint32_t* __restrict__ fb0, int resX, int resY, const int* __restrict__ list, const int* __restrict__ listCount,
                          LineRec* __restrict__ recH, LineRec* __restrict__ recV, int* __restrict__ cntH, int* __restrict__ cntV,
@@ -328,7 +190,7 @@ mlaa_line_records_kernel(const uint32_t* __restrict__ fb0, int resX, int resY, c
 {
     const int n = *listCount;
     for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < n; i += (int)(gridDim.x * blockDim.x))
-        line_record(fb0, resX, resY, list[i], recH, recV, cntH, cntV, endH, endV, capH, capV);
+        line_record<BATCH>(fb0, resX, resY, list[i], recH, recV, cntH, cntV, endH, endV, capH, capV);
 }
 
 __global__ void mlaa_lines_reset_kernel(int* __restrict__ cnt, int* __restrict__ lastEnd, int n, int* __restrict__ listCount)
@@ -339,6 +201,7 @@ __global__ void mlaa_lines_reset_kernel(int* __restrict__ cnt, int* __restrict__
 }
 
 // The ordered part: one CTA per 8-row (8-column) block of the given parity, rows in order, one thread per line record.
+template <int BATCH>
 __global__ void __launch_bounds__(256)
 mlaa_blend_lines_kernel(uint32_t* fbi, const uint32_t* __restrict__ fb0, int resX, int resY, int vertical, int yodd,
                         const LineRec* __restrict__ rec, const int* __restrict__ cnt, const int* __restrict__ lastEnd, int cap)
@@ -358,15 +221,7 @@ mlaa_blend_lines_kernel(uint32_t* fbi, const uint32_t* __restrict__ fb0, int res
         const int n = min(cnt[row], cap);
         const LineRec* rr = rec + (size_t)row * cap;
         for (int i = (int)threadIdx.x; i < n; i += (int)blockDim.x) {
-            const LineRec r = rr[i];
-            if (r.ui1 == -2) { blend_one_cell(fbi, r.ui0, after); continue; }
-            bool done = false;
-            if (r.ui0 != -1 && r.li1 != -1 && r.ui0 < r.li1) { blendInterval(fbi, r.ui0, r.li1, r.uh0, r.lh1, stepx, after, false); done = true; }
-            if (r.li0 != -1 && r.ui1 != -1 && r.li0 < r.ui1) { blendInterval(fbi, r.li0, r.ui1, r.lh0, r.uh1, stepx, befor, false); done = true; }
-            if (!done) {
-                if (r.ui0 != -1 && r.ui1 != -1 && r.ui0 < r.ui1) blendInterval(fbi, r.ui0, r.ui1, r.uh0, r.uh1, stepx, after, true);
-                if (r.li0 != -1 && r.li1 != -1 && r.li0 < r.li1) blendInterval(fbi, r.li0, r.li1, r.lh0, r.lh1, stepx, befor, true);
-            }
+            mlaa_line_blend<BATCH>(fbi, rr[i], stepx, befor, after);
         }
         __syncthreads();
         // the SSE scan quirk of the horizontal search (see mlaa_blend_kernel), applied after all lines of this row
@@ -376,7 +231,7 @@ mlaa_blend_lines_kernel(uint32_t* fbi, const uint32_t* __restrict__ fb0, int res
                 const int base = row * stepy + resx;
                 for (int q = 0; q < 4; q++)
                     if (fb0[base + q] & HF) {
-                        if (base + q + after < sz) blend_one_cell(fbi, base + q, after);
+                        if (base + q + after < sz) mlaa_blend_one_cell(fbi, base + q, after);
                         break;
                     }
             }
@@ -413,24 +268,28 @@ cudaError_t launch_mlaa(uint32_t* d_frame, uint32_t* d_scratch, int resX, int re
         int* cntV = cntH + resY; int* endH = cntV + resX; int* endV = endH + resY;
         int* listCount = endV + resX; int* list = listCount + 4;
         mlaa_lines_reset_kernel<<<(resX + resY + 255) / 256, 256, 0, st>>>(cntH, endH, resX + resY, listCount);   // cntH|cntV and endH|endV are contiguous
+        // batched flag / pixel loads need runs shorter than a row/column by a wide margin (mlaa_steps.h); tiny frames walk step by step
+        const bool batch = resX >= 4 * BLEND_BATCH && resY >= 4 * BLEND_BATCH && !getenv("B200R_MLAA_NOBATCH");
         const bool fullScan = getenv("B200R_MLAA_FULLSCAN") != nullptr;
         if (fullScan) mlaa_lines_kernel<<<numSMs * 8, 256, 0, st>>>(d_scratch, resX, resY, recH, recV, cntH, cntV, endH, endV, capH, capV);
         else {
             mlaa_line_starts_kernel<<<numSMs * 8, 256, 0, st>>>(d_scratch, resX, resY, list, listCount);
-            mlaa_line_records_kernel<<<numSMs * 8, 128, 0, st>>>(d_scratch, resX, resY, list, listCount, recH, recV, cntH, cntV, endH, endV, capH, capV);
+            auto records = batch ? mlaa_line_records_kernel<BLEND_BATCH> : mlaa_line_records_kernel<1>;
+            records<<<numSMs * 8, 128, 0, st>>>(d_scratch, resX, resY, list, listCount, recH, recV, cntH, cntV, endH, endV, capH, capV);
             launches += 1;
         }
-        if (h0 > 0) mlaa_blend_lines_kernel<<<h0, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 0, 0, recH, cntH, endH, capH);
-        if (h1 > 0) mlaa_blend_lines_kernel<<<h1, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 0, 1, recH, cntH, endH, capH);
-        if (v0 > 0) mlaa_blend_lines_kernel<<<v0, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 1, 0, recV, cntV, endV, capV);
-        if (v1 > 0) mlaa_blend_lines_kernel<<<v1, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 1, 1, recV, cntV, endV, capV);
+        auto blend = batch ? mlaa_blend_lines_kernel<BLEND_BATCH> : mlaa_blend_lines_kernel<1>;
+        if (h0 > 0) blend<<<h0, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 0, 0, recH, cntH, endH, capH);
+        if (h1 > 0) blend<<<h1, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 0, 1, recH, cntH, endH, capH);
+        if (v0 > 0) blend<<<v0, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 1, 0, recV, cntV, endV, capV);
+        if (v1 > 0) blend<<<v1, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 1, 1, recV, cntV, endV, capV);
         launches += 7;
         return cudaGetLastError();
     }
-    if (h0 > 0) mlaa_blend_kernel<<<h0, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 0, 0);
-    if (h1 > 0) mlaa_blend_kernel<<<h1, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 0, 1);
-    if (v0 > 0) mlaa_blend_kernel<<<v0, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 1, 0);
-    if (v1 > 0) mlaa_blend_kernel<<<v1, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 1, 1);
+    if (h0 > 0) mlaa_blend_kernel<1><<<h0, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 0, 0);
+    if (h1 > 0) mlaa_blend_kernel<1><<<h1, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 0, 1);
+    if (v0 > 0) mlaa_blend_kernel<1><<<v0, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 1, 0);
+    if (v1 > 0) mlaa_blend_kernel<1><<<v1, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 1, 1);
     launches += 5;
     return cudaGetLastError();
 }

@@ -85,3 +85,43 @@ def test_default_lights(rb):
     l0, l1 = rb.default_light_pos(0), rb.default_light_pos(1)
     assert np.allclose(l0, (3.394113, 3.394113, 4.8), atol=1e-5)
     assert np.allclose(l1, (4.8, -4.8, 4.8), atol=1e-6)
+
+
+@pytest.mark.parametrize("model,mode,size,frame", [("statue.ply", 6, (320, 240), 0), ("statue.ply", 5, (640, 480), 37),
+                                                   ("chessboard.tri", 6, (400, 304), 9), ("torus.ply", 4, (64, 48), 3),
+                                                   ("dragon_vis.ply", 6, (1280, 720), 1)])
+def test_mlaa_step_functions_equal_the_oracle(rb, pyport, model, mode, size, frame):
+    """csrc/mlaa_steps.h - the per-item functions the MLAA kernels are made of (flags, line bounds, split heights, the in-place
+    blends; with and without the 8-pixel batched loads the device uses) - run in plain loops in the kernels' job order:
+    the filtered frame equals the restatement of the reference's MLAA (itself pinned to the reference's goldens) bit for bit."""
+    import ctypes as C
+    path = pyport.model_path(model)
+    if not os.path.exists(path):
+        pytest.skip("model not staged")
+    s = rb.Scene(path)
+    cam = rb.Orbit.cameras([frame])[frame]
+    plain = pyport.render(s, rb.make_frame(mode, size[0], size[1], cam))
+    want = pyport.mlaa(plain)
+    assert 0 < int((want != plain).sum())
+    for batched in (0, 1):
+        got = np.ascontiguousarray(plain, dtype=np.uint32).copy()
+        rc = rb.lib().b200r_selftest_mlaa_steps_host(got.ctypes.data, size[0], size[1], batched)
+        assert rc == 0
+        assert np.array_equal(got, want), f"batched={batched}: {int((got != want).sum())} pixels differ"
+
+
+def test_mlaa_step_functions_on_noise(rb, pyport):
+    """Random blocky frames (every kind of L/Z/U shape, lines touching all four borders, runs up to a full row) through the
+    same comparison: batched == unbatched == oracle."""
+    rng = np.random.default_rng(7)
+    for W, H, cell in ((64, 48, 1), (128, 96, 3), (256, 64, 8), (96, 256, 5), (512, 384, 16)):
+        coarse = rng.integers(0, 4, size=((H + cell - 1) // cell, (W + cell - 1) // cell), dtype=np.uint32)
+        palette = np.array([0x00101010, 0x00E0E0E0, 0x00FF2040, 0x0020C0FF], dtype=np.uint32)
+        img = np.kron(palette[coarse], np.ones((cell, cell), dtype=np.uint32))[:H, :W].astype(np.uint32)
+        img[H // 3, :] = 0x00FFFFFF                    # a separation line as long as the row
+        img[:, W // 5] = 0x00000000                    # ... and one as long as the column
+        want = pyport.mlaa(img)
+        for batched in (0, 1):
+            got = np.ascontiguousarray(img).copy()
+            assert rb.lib().b200r_selftest_mlaa_steps_host(got.ctypes.data, W, H, batched) == 0
+            assert np.array_equal(got, want), f"{W}x{H} cell {cell} batched={batched}: {int((got != want).sum())} pixels differ"

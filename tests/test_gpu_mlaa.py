@@ -40,6 +40,10 @@ def test_mlaa_vs_oracle(rb, pyport, load_scene, gpu, monkeypatch, model, mode, s
     full = gpu.render(f)                                 # two-stage, but the scanning thread also walks the line it finds
     monkeypatch.delenv("B200R_MLAA_FULLSCAN")
     assert np.array_equal(got, full)
+    monkeypatch.setenv("B200R_MLAA_NOBATCH", "1")
+    stepwise = gpu.render(f)                             # flag / pixel words loaded one step at a time, as the reference's loops do
+    monkeypatch.delenv("B200R_MLAA_NOBATCH")
+    assert np.array_equal(got, stepwise)
     plain = gpu.render(rb.make_frame(mode, size[0], size[1], cam))
     assert 0 < int((plain != got).sum()) < 0.2 * got.size       # the filter touches edges only
 
