@@ -199,6 +199,11 @@ int  b200r_selftest_bvh_steps_host(const b200r_vertex* verts, uint32_t n_verts, 
  * bounds, split heights, in-place blends - `batched` != 0: with the 8-pixel batched loads the device uses) run in plain
  * loops on the host, in place on a width x height frame. Not a rendering path. */
 int  b200r_selftest_mlaa_steps_host(uint32_t* frame_xrgb, uint32_t width, uint32_t height, int batched);
+/* Test hook (no device needed): the span walkers of csrc/raster_steps.h (what the depth / resolve passes run per span,
+ * pixel by pixel and with 8 depth keys requested together) over n_spans random spans against the per-scanline loop of
+ * Screen::RasterizeTriangle (src/Screen.h:244-289) as written there: *mismatches = spans whose pixel sequence (x, interpolant
+ * bits, key) differs. Not a rendering path. */
+int  b200r_selftest_span_walk_host(uint32_t seed, uint32_t n_spans, uint32_t width, uint64_t* mismatches);
 
 
 /* Numerics self-test: the slab test's shared-reciprocal divide (DESIGN.md "division") against the compiler's IEEE

@@ -79,6 +79,7 @@ SYMBOLS = {
                                   P(C.c_int32), P(C.c_uint32), P(C.c_int32)]),
     "b200r_selftest_bvh_steps_host": (C.c_int, [P(Vertex), C.c_uint32, P(Tri), C.c_uint32, P(BvhNode), C.c_uint32,
                                                 P(C.c_int32), P(C.c_uint32), P(C.c_int32)]),
+    "b200r_selftest_span_walk_host": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, P(C.c_uint64)]),
     "b200r_selftest_mlaa_steps_host": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]),
     "b200r_set_tile_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "b200r_get_tile_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, P(C.c_uint32)]),

@@ -23,6 +23,7 @@
 
 #include "device_types.cuh"
 #include "rt_kernels.cuh"
+#include "../raster_steps.h"
 
 namespace b200r {
 
@@ -32,21 +33,7 @@ constexpr float kClipPlaneDistance = 0.2f;        // reference src/Rasterizers.c
 constexpr int SMAP = B200R_SHADOWMAP_SIZE;
 constexpr int SPAN_WORDS = 20;                     // tri, y|flags, 8+8 interpolants (+2 pad): five 16-byte chunks
 
-template <int N> struct FPd { float v[N]; };
 struct Mat9 { float m[9]; };
-
-template <int N> __device__ __forceinline__ void fp_add(FPd<N>& a, const FPd<N>& b)
-{
-#pragma unroll
-    for (int i = 0; i < N; i++) a.v[i] += b.v[i];
-}
-
-// Screen::myfloor (reference src/Screen.h:218-221) with x86 float->int conversion semantics
-__device__ __forceinline__ int myfloor_x86(float val)
-{
-    if (val < 0.f) return cvtt_x86(val - 0.5f);
-    return cvtt_x86(val + 0.5f);
-}
 
 // ---- one edge of ScanConverter::ScanConvert / InnerLoop (reference src/ScanConverter.h:90-136)
 template <int N>
@@ -342,44 +329,8 @@ __device__ __forceinline__ void load_span(const uint32_t* __restrict__ spans, un
     for (int i = 0; i < N; i++) { L.v[i] = buf[i]; R.v[i] = buf[8 + i]; }
 }
 
-// The per-scanline body of Screen::RasterizeTriangle (reference src/Screen.h:244-289): calls frag(x, v) per pixel.
-template <int N, class Frag>
-__device__ __forceinline__ void walk_span(int W, bool single, const FPd<N>& L, const FPd<N>& R, Frag&& frag)
-{
-    if (single) {
-        const int x = myfloor_x86(L.v[0]);
-        if (x < 0 || x >= W) return;
-        frag(x, L);
-        return;
-    }
-    int x1 = myfloor_x86(L.v[0]); if (x1 >= W) return;
-    const int x2 = myfloor_x86(R.v[0]); if (x2 < 0) return;
-    int steps = abs(x2 - x1);
-    if (!steps) {
-        const int x = myfloor_x86(L.v[0]);
-        if (x < 0 || x >= W) return;
-        frag(x, L);
-        return;
-    }
-    FPd<N> start = L, dLR;
-    const float fs = (float)steps;
-#pragma unroll
-    for (int i = 0; i < N; i++) { float t = R.v[i]; t -= start.v[i]; t /= fs; dLR.v[i] = t; }
-    if (x1 < 0) {
-        const float k = (float)-x1;
-#pragma unroll
-        for (int i = 0; i < N; i++) { float t = dLR.v[i]; t *= k; start.v[i] += t; }
-        steps -= (-x1);
-        x1 = 0;
-    }
-    if (x2 >= W) steps -= (x2 - W + 1);
-    frag(x1, start);
-    while (steps-- > 0) {
-        x1++;
-        fp_add<N>(start, dLR);
-        frag(x1, start);
-    }
-}
+// (walk_span / walk_span_keyed: csrc/raster_steps.h)
+constexpr int KEY_BATCH = 8;      // depth keys requested together by the resolve passes
 
 __device__ __forceinline__ unsigned long long depth_key(float z, uint32_t tri)
 {
@@ -424,9 +375,10 @@ ras_resolve_kernel(DeviceScene sc, FrameParams fp, const uint32_t* __restrict__ 
         load_span<N>(spans, s, tri, y, single, empty, L, R);
         if (empty) continue;
         const size_t rowOff = (size_t)((y - (int)fp.row_first) / (int)fp.row_step) * W;
-        walk_span<N>(W, single, L, R, [&](int x, const FPd<N>& v) {
+        walk_span_keyed<N, KEY_BATCH>(W, single, L, R, [&](int x) { return zkeys[rowOff + x]; },
+                                      [&](int x, const FPd<N>& v, unsigned long long stored) {
             const float z = v.v[N == 5 ? 1 : 3];
-            if (z > 0.f && zkeys[rowOff + x] == depth_key(z, tri)) {
+            if (z > 0.f && stored == depth_key(z, tri)) {
                 out[rowOff + x] = shade_fragment<N, LM>(sc, fp, v, tri);
                 wins++;
             }
@@ -453,9 +405,10 @@ ras_resolve_attr_kernel(FrameParams fp, const uint32_t* __restrict__ spans, cons
         load_span<N>(spans, s, tri, y, single, empty, L, R);
         if (empty) continue;
         const size_t rowOff = (size_t)((y - (int)fp.row_first) / (int)fp.row_step) * W;
-        walk_span<N>(W, single, L, R, [&](int x, const FPd<N>& v) {
+        walk_span_keyed<N, KEY_BATCH>(W, single, L, R, [&](int x) { return zkeys[rowOff + x]; },
+                                      [&](int x, const FPd<N>& v, unsigned long long stored) {
             const float z = v.v[3];
-            if (z > 0.f && zkeys[rowOff + x] == depth_key(z, tri)) {
+            if (z > 0.f && stored == depth_key(z, tri)) {
                 float4* a = attrs + 2 * (rowOff + x);
                 a[0] = make_float4(v.v[1], v.v[2], v.v[3], v.v[4]);
                 a[1] = make_float4(v.v[5], v.v[6], v.v[7], 0.f);

@@ -125,3 +125,14 @@ def test_mlaa_step_functions_on_noise(rb, pyport):
             got = np.ascontiguousarray(img).copy()
             assert rb.lib().b200r_selftest_mlaa_steps_host(got.ctypes.data, W, H, batched) == 0
             assert np.array_equal(got, want), f"{W}x{H} cell {cell} batched={batched}: {int((got != want).sum())} pixels differ"
+
+
+@pytest.mark.parametrize("width", [8, 64, 800, 3840])
+def test_span_walkers_equal_the_reference_loop(rb, width):
+    """csrc/raster_steps.h: walk_span and the batched walk_span_keyed (8 depth keys requested together, what the device's
+    resolve passes run per span) visit the pixels of Screen::RasterizeTriangle's loop with the same interpolant bits -
+    random spans incl. single-point, zero-length, clipped left / right / both."""
+    import ctypes as C
+    bad = C.c_uint64(123)
+    assert rb.lib().b200r_selftest_span_walk_host(width + 1, 40000, width, C.byref(bad)) == 0
+    assert bad.value == 0
