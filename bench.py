@@ -236,16 +236,19 @@ def cpu_reference(wl, target_seconds=15.0, rays_per_frame=None, runner=None):
             "sample": f"{n} orbit frames of [{wl['desc']}] by oracle/port (C++ restatement, OpenMP over rows)"}
 
 
-def port_rays_per_frame(wl, frame=0):
-    """Rays (BVH_IntersectTriangles invocations) of one orbit frame, counted by the CPU restatement."""
+def port_rays_per_frame(wl, frames=(0,)):
+    """Rays (BVH_IntersectTriangles invocations) per orbit frame, counted by the CPU restatement: mean over `frames`."""
     import renderer_b200 as rb
     from oracle import pyport
     model = pyport.model_path(wl["model"])
     scene = rb.Scene(model).UpdateBoundingVolumeHierarchy(model + ".bvh")
-    cam = rb.Orbit.cameras([frame])[frame]
-    f = rb.make_frame(wl["mode"], wl["W"], wl["H"], cam, flags=wl["flags"], ao_samples=wl["ao"] or 32, frame_index=frame)
-    _, c = pyport.render(scene, f, counters=True)
-    return c["rays_primary"] + c["rays_shadow"] + c["rays_reflection"] + c["rays_ao"]
+    cams = rb.Orbit.cameras(range(max(frames) + 1))
+    total = 0
+    for k in frames:
+        f = rb.make_frame(wl["mode"], wl["W"], wl["H"], cams[k], flags=wl["flags"], ao_samples=wl["ao"] or 32, frame_index=k)
+        _, c = pyport.render(scene, f, counters=True)
+        total += c["rays_primary"] + c["rays_shadow"] + c["rays_reflection"] + c["rays_ao"]
+    return total / len(frames)
 
 
 def run_reference_arm(args, wl):
@@ -254,7 +257,9 @@ def run_reference_arm(args, wl):
         return
     t0 = time.time()
     raster = bool(wl.get("raster"))
-    rays = 0 if raster else port_rays_per_frame(wl)
+    # rays per frame: mean over five frames spread over the orbit frames the B200 arm times (warmup .. warmup+steps-1)
+    K, Wm = max(1, args.steps), args.warmup
+    rays = 0 if raster else port_rays_per_frame(wl, frames=sorted({Wm + (K - 1) * q // 4 for q in range(5)}))
     # each "step" is a bounded sample: the reference renders a batch of orbit frames; K+W batches in total
     per_step = max(1.5, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
     vals = []
