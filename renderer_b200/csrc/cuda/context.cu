@@ -824,6 +824,18 @@ int b200r_get_tile_profile(b200r_ctx* ctx, uint64_t* start_end_ns, uint32_t max_
     return B200R_OK;
 }
 
+int b200r_get_warp_profile(b200r_ctx* ctx, uint32_t scratch_slot, uint64_t* records, uint32_t max_warps, uint32_t* n_warps)
+{
+    if (!ctx || !n_warps || scratch_slot >= B200R_MAX_FRAMES_IN_FLIGHT) return fail(ctx, B200R_EINVAL, "b200r_get_warp_profile: bad argument");
+    const RtBuffers& rt = ctx->rts[scratch_slot];
+    *n_warps = rt.warpProf ? rt.lastPrimaryWarps : 0u;
+    if (!records || !rt.warpProf) return B200R_OK;
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t n = *n_warps < max_warps ? *n_warps : max_warps;
+    CU(cudaMemcpy(records, rt.warpProf, (size_t)n * 32, cudaMemcpyDeviceToHost));      // synchronises with the device
+    return B200R_OK;
+}
+
 int b200r_set_counters(b200r_ctx* ctx, int enabled)
 {
     if (!ctx) return fail(nullptr, B200R_EINVAL, "NULL ctx");
