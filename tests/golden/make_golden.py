@@ -52,6 +52,36 @@ CASES = {
 }
 
 
+# BASELINE.json's configurations at their FULL sizes (frames {0, 1, 37, 99} of the -b orbit). A 4K frame is
+# 33 MB, so only the SHA-256 (and the count of non-black pixels) is stored: tests compare digests; on a mismatch the CPU
+# restatement (pinned to the same digests) supplies the pixels to diff against.
+# name: (model, mode, width, height, frames, variant kwargs, env)
+FULL_FRAMES = [0, 1, 37, 99]
+FULL_CASES = {
+    "full_c2_chess_m9_norefl": ("chessboard.tri", 9, 1920, 1080, FULL_FRAMES, {"no_reflections": True}, {}),
+    "full_c3_dragon_m9_ao16": ("dragon_vis.ply", 9, 1920, 1080, FULL_FRAMES, {"ao": 16}, {"OMP_NUM_THREADS": "8"}),
+    "full_c4_statue_m5_mlaa": ("statue.ply", 5, 3840, 2160, FULL_FRAMES, {"mlaa": True}, {"OMP_NUM_THREADS": "1"}),
+    "full_c4_statue_m6_mlaa": ("statue.ply", 6, 3840, 2160, FULL_FRAMES, {"mlaa": True}, {"OMP_NUM_THREADS": "1"}),
+    "full_c5_chess_m9_ao16": ("chessboard.tri", 9, 3840, 2160, FULL_FRAMES, {"ao": 16}, {"OMP_NUM_THREADS": "8"}),
+}
+
+
+def full_size(only, index):
+    import time
+    for name, (model, mode, w, h, frames, kw, env) in FULL_CASES.items():
+        if only and name not in only:
+            continue
+        if not pyport.have_ref(w, h, **kw):
+            pyport.build_ref(w, h, **kw)
+        t0 = time.time()
+        imgs, _ = pyport.run_ref(pyport.model_path(model), mode, w, h, frames, env=env, **kw)
+        index[name] = {"model": model, "mode": mode, "frames": frames, "two_lights": False, "variant": kw,
+                       "width": w, "height": h, "digest_only": True,
+                       "lit_pixels": {str(k): int((v != 0).sum()) for k, v in imgs.items()},
+                       "sha256": {str(k): hashlib.sha256(v.tobytes()).hexdigest() for k, v in imgs.items()}}
+        print(name, index[name]["lit_pixels"], f"{time.time() - t0:.1f} s")
+
+
 def main():
     only = set(sys.argv[1:])
     index_path = os.path.join(HERE, "index.json")
@@ -68,14 +98,15 @@ def main():
                        "width": W, "height": H,
                        "sha256": {str(k): hashlib.sha256(v.tobytes()).hexdigest() for k, v in imgs.items()}}
         print(name, {k: int((v != 0).sum()) for k, v in imgs.items()})
+    full_size(only, index)
     # the reference's own .bvh caches (byte-level pin of loader + BVH builder)
     bvh = {}
     for m in sorted(os.listdir(pyport.MODELS)):
         p = os.path.join(pyport.MODELS, m + "") if m.endswith(".bvh") else None
         if p:
             bvh[m[:-4]] = hashlib.sha256(open(p, "rb").read()).hexdigest()
-    if bvh:
-        index["_bvh_sha256"] = bvh
+    if bvh:                      # merge: only the caches the reference wrote during THIS run are in the directory
+        index.setdefault("_bvh_sha256", {}).update(bvh)
     json.dump(index, open(index_path, "w"), indent=1, sort_keys=True)
 
 
