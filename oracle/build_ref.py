@@ -54,6 +54,8 @@ def tag_of(a):
         t += "_mlaa"
     if a.fast:
         t += "_fast"
+    if getattr(a, "libc_rand", False):
+        t += "_libcrand"
     return t
 
 
@@ -131,11 +133,13 @@ def build(a):
         if a.ao:
             sub_exact(rt, r"^//#define AMBIENT_OCCLUSION\s*$", "#define AMBIENT_OCCLUSION")
             sub_exact(rt, r"^#define AMBIENT_SAMPLES\s+32\s*$", f"#define AMBIENT_SAMPLES {a.ao}")
-            # the single permitted semantic delta: seed the per-pixel random stream
-            sub_exact(rt, r"^(\s*for\(int x=xStarting; x<iOnePastEndingX; x\+\+\) \{)\s*$",
-                      r"\1 oracle_seed(x, y);")
-            # ... and draw from it instead of the process-global, racy libc rand() (3 call sites, :393-395)
-            sub_exact(rt, r"float\(rand\(\)-RAND_MAX/2\)", "float(oracle_rand()-RAND_MAX/2)", count=3)
+            if not a.libc_rand:
+                # the single permitted semantic delta: seed the per-pixel random stream
+                sub_exact(rt, r"^(\s*for\(int x=xStarting; x<iOnePastEndingX; x\+\+\) \{)\s*$",
+                          r"\1 oracle_seed(x, y);")
+                # ... and draw from it instead of the process-global, racy libc rand() (3 call sites, :393-395)
+                sub_exact(rt, r"float\(rand\(\)-RAND_MAX/2\)", "float(oracle_rand()-RAND_MAX/2)", count=3)
+            # (--libc-rand: AO exactly as the reference has it, libc rand() and all - for the statistical comparison only)
 
         flags = FAST_FLAGS if a.fast else STRICT_FLAGS
         inc = ["-I", work, "-I", STUB, "-I", os.path.join(REF, "lib3ds-1.3.0")]
@@ -188,6 +192,8 @@ def main():
     ap.add_argument("--ao", type=int, default=0, help="enable AMBIENT_OCCLUSION with N samples")
     ap.add_argument("--mlaa", action="store_true")
     ap.add_argument("--fast", action="store_true", help="reference's own flags (timing baseline)")
+    ap.add_argument("--libc-rand", action="store_true",
+                    help="with --ao: keep the reference's libc rand() (not reproducible in parallel; statistics only)")
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--stage-models", action="store_true")
     a = ap.parse_args()

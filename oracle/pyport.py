@@ -130,7 +130,7 @@ def mlaa(frame_u32):
 
 # ---------------------------------------------------------------- the real reference, built headless
 
-def ref_tag(w, h, no_reflections=False, ao=0, mlaa=False, fast=False):
+def ref_tag(w, h, no_reflections=False, ao=0, mlaa=False, fast=False, libc_rand=False):
     t = f"{w}x{h}"
     if no_reflections:
         t += "_norefl"
@@ -140,6 +140,8 @@ def ref_tag(w, h, no_reflections=False, ao=0, mlaa=False, fast=False):
         t += "_mlaa"
     if fast:
         t += "_fast"
+    if libc_rand:
+        t += "_libcrand"
     return t
 
 
@@ -151,7 +153,7 @@ def have_ref(w, h, **kw):
     return os.path.exists(ref_exe(w, h, **kw))
 
 
-def build_ref(w, h, no_reflections=False, ao=0, mlaa=False, fast=False):
+def build_ref(w, h, no_reflections=False, ao=0, mlaa=False, fast=False, libc_rand=False):
     """Only possible where /root/reference is mounted (not on the GPU box)."""
     cmd = [sys.executable, os.path.join(HERE, "build_ref.py"), "--w", str(w), "--h", str(h)]
     if no_reflections:
@@ -162,8 +164,10 @@ def build_ref(w, h, no_reflections=False, ao=0, mlaa=False, fast=False):
         cmd.append("--mlaa")
     if fast:
         cmd.append("--fast")
+    if libc_rand:
+        cmd.append("--libc-rand")
     subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
-    return ref_exe(w, h, no_reflections=no_reflections, ao=ao, mlaa=mlaa, fast=fast)
+    return ref_exe(w, h, no_reflections=no_reflections, ao=ao, mlaa=mlaa, fast=fast, libc_rand=libc_rand)
 
 
 def model_path(name):

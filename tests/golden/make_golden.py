@@ -82,6 +82,41 @@ def full_size(only, index):
         print(name, index[name]["lit_pixels"], f"{time.time() - t0:.1f} s")
 
 
+# The AO caveat of SURVEY.md section 8c: the parity oracle draws AO samples from a per-pixel seeded stream (the one permitted
+# delta). These cases keep the reference's libc rand() (single thread, so the run is repeatable) - NOT parity targets, only the
+# other side of a statistical comparison: same image up to sampling noise, no bias.
+STAT_CASES = {
+    "stat_chess_m9_ao16_libcrand": ("chessboard.tri", 9, [2], {"ao": 16, "libc_rand": True}, {"OMP_NUM_THREADS": "1"}, "rt_chess_m9_ao16"),
+    "stat_torus_m9_ao16_libcrand": ("torus.ply", 9, [2], {"ao": 16, "libc_rand": True}, {"OMP_NUM_THREADS": "1"}, "rt_torus_m9_ao16"),
+}
+
+
+def channels(img):
+    return np.stack([(img >> 16) & 255, (img >> 8) & 255, img & 255], -1).astype(np.int32)
+
+
+def ao_statistics(only, index):
+    for name, (model, mode, frames, kw, env, seeded_case) in STAT_CASES.items():
+        if only and name not in only:
+            continue
+        if not pyport.have_ref(W, H, **kw):
+            pyport.build_ref(W, H, **kw)
+        imgs, _ = pyport.run_ref(pyport.model_path(model), mode, W, H, frames, env=env, **kw)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **{f"frame_{k}": v for k, v in imgs.items()})
+        seeded = np.load(os.path.join(HERE, seeded_case + ".npz"))
+        stats = {}
+        for k, b in imgs.items():
+            a = seeded[f"frame_{k}"]
+            lit = (a != 0) | (b != 0)
+            ca, cb = channels(a)[lit], channels(b)[lit]
+            stats[str(k)] = {"lit_pixels": int(lit.sum()), "mean_abs_diff": round(float(np.abs(ca - cb).mean()), 3),
+                             "max_abs_diff": int(np.abs(ca - cb).max()), "mean_level_seeded_stream": round(float(ca.mean()), 2),
+                             "mean_level_libc_rand": round(float(cb.mean()), 2)}
+        index[name] = {"model": model, "mode": mode, "frames": frames, "two_lights": False, "variant": kw, "width": W, "height": H,
+                       "statistical": True, "seeded_case": seeded_case, "vs_seeded_stream": stats}
+        print(name, stats)
+
+
 def main():
     only = set(sys.argv[1:])
     index_path = os.path.join(HERE, "index.json")
@@ -99,6 +134,7 @@ def main():
                        "sha256": {str(k): hashlib.sha256(v.tobytes()).hexdigest() for k, v in imgs.items()}}
         print(name, {k: int((v != 0).sum()) for k, v in imgs.items()})
     full_size(only, index)
+    ao_statistics(only, index)
     # the reference's own .bvh caches (byte-level pin of loader + BVH builder)
     bvh = {}
     for m in sorted(os.listdir(pyport.MODELS)):
