@@ -271,7 +271,9 @@ def run_reference_arm(args, wl):
     fps = sum(v["fps"] for v in vals) / len(vals)
     unit = "fps" if raster else "Mrays/s"
     val = fps if raster else rays * fps / 1e6
+    per_step = sorted(v["fps"] for v in vals)
     cb = dict(vals[-1]); cb["value"] = val; cb["fps"] = fps
+    cb["fps_median"] = per_step[len(per_step) // 2]; cb["fps_best"] = per_step[-1]; cb["fps_worst"] = per_step[0]
     line = {"impl": "reference", "metric": unit, "value": val, "unit": unit, "fps": fps, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / fps if fps else None,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
