@@ -159,13 +159,13 @@ static void expand(const Scene& sc, const V3& o, const V3& d, uint32_t root, int
 
 // donateAfter > 0: a job that has run that many steps hands the BOTTOM entry of its stack (its largest pending subtree) to a new
 // job every step from then on (what rt_primary_kernel's donation does once the queue is empty, here: always, to unlimited lanes)
-struct Policy { int split; bool shared; int shadowSplit; int donateAfter; const char* name; };
+struct Policy { int split; bool shared; int shadowSplit; int donateAfter; const char* name; bool needHit = false; bool shadowDonate = true; };
 
 // Lock-step execution of the jobs of one ray: every running job advances one step per round; with donation, a job that has run
 // `donateAfter` steps gives its bottom stack entry to a new job (same ray, same shared state) that starts in the next round.
 // Returns the number of rounds = the length of the ray's dependency chain under that policy.
 struct Priv { float best; uint32_t li; int tri; V3 hit; };
-static int run(std::vector<Job>& jobs, int donateAfter, std::deque<Priv>* priv = nullptr)
+static int run(std::vector<Job>& jobs, int donateAfter, std::deque<Priv>* priv = nullptr, bool needHit = false)
 {
     int rounds = 0;
     for (bool any = true; any;) {
@@ -174,7 +174,8 @@ static int run(std::vector<Job>& jobs, int donateAfter, std::deque<Priv>* priv =
         for (size_t j = 0; j < n; j++) {
             if (jobs[j].done) continue;
             jobs[j].step(); any = true;
-            if (donateAfter > 0 && !jobs[j].done && jobs[j].steps >= donateAfter && !jobs[j].stack.empty()) {
+            if (donateAfter > 0 && !jobs[j].done && jobs[j].steps >= donateAfter && !jobs[j].stack.empty() &&
+                (jobs[j].shadow || !needHit || *jobs[j].best < FLT_MAX)) {
                 const auto entry = jobs[j].stack.front();
                 jobs[j].stack.erase(jobs[j].stack.begin());
                 Job D = jobs[j];                       // same ray, same pointers to the shared state
@@ -236,6 +237,9 @@ int main(int argc, char** argv)
         {2, true, 0, 16, "split 2 shared, donate after 16 steps"},
         {2, true, 0, 8, "split 2 shared, donate after 8 steps"},
         {2, true, 2, 16, "split 2 shared, shadow split 2, donate after 16 steps"},
+        {2, false, 0, 32, "split 2 NOT shared, primary jobs with a hit donate after 32 steps (= B200R_URGENT_T=32)", true, false},
+        {2, false, 0, 16, "split 2 NOT shared, primary jobs with a hit donate after 16 steps (= B200R_URGENT_T=16)", true, false},
+        {2, false, 0, 32, "split 2 NOT shared, primary jobs donate after 32 steps, hit or not (= B200R_URGENT_T=32 B200R_URGENT_NOHIT=1)", false, false},
         {2, false, 0, 32, "split 2 NOT shared, donate after 32 steps (a donated part starts from its donor's bound only)"},
         {2, false, 0, 16, "split 2 NOT shared, donate after 16 steps"},
     };
@@ -273,7 +277,7 @@ int main(int argc, char** argv)
                     }
                     // lock-step: every running job advances one step per round (sharing, if on, is then immediate)
                     std::deque<Priv> priv;
-                    int longest = run(jobs, P.donateAfter, P.shared ? nullptr : &priv);
+                    int longest = run(jobs, P.donateAfter, P.shared ? nullptr : &priv, P.needHit);
                     for (const Priv& p : priv)
                         if (p.tri >= 0 && (p.best < best || (p.best == best && p.li < bestLi))) { best = p.best; bestLi = p.li; bestTri = p.tri; bestHit = p.hit; }
                     for (size_t j = subs.size(); j < jobs.size(); j++) { T.steps += jobs[j].steps; T.jobs++; }     // donated parts
@@ -303,7 +307,7 @@ int main(int argc, char** argv)
                                     J.best = &best; J.bestLi = &bestLi; J.bestTri = &bestTri; J.bestHit = &bestHit;
                                     J.init(&sc, bestHit, sd, ssubs[j]);
                                 }
-                                shadowLongest = run(sjobs, P.donateAfter);
+                                shadowLongest = run(sjobs, P.shadowDonate ? P.donateAfter : 0);
                                 for (const Job& J : sjobs) { T.steps += J.steps; T.jobs++; }
                                 T.shadowRays++;
                                 if (P.shadowSplit == 0) (occ ? T.shadowBlocked : T.shadowLit).push_back(sjobs[0].steps);
