@@ -216,11 +216,11 @@ int  b200r_selftest_division(b200r_ctx* ctx, uint64_t samples, uint32_t seed, ui
 int  b200r_set_tile_profile(b200r_ctx* ctx, int enabled);
 int  b200r_get_tile_profile(b200r_ctx* ctx, uint64_t* start_end_ns, uint32_t max_tiles, uint32_t* n_tiles);
 
-/* Developer tool (environment B200R_WARP_PROFILE=1 while rendering): the per-warp records of the last ray-traced frame rendered
- * with scratch set `scratch_slot` - 4 x uint64 per warp of the persistent kernel: globaltimer at begin, at end, packed ray /
- * shadow-ray / donation counts, packed rounds / refills / time the job queue ran dry (tools/warp_profile.py decodes them).
- * Absolute times: records of frames that were in flight together (b200r_render_device_slot) share one time axis. */
-int  b200r_get_warp_profile(b200r_ctx* ctx, uint32_t scratch_slot, uint64_t* records, uint32_t max_warps, uint32_t* n_warps);
+/* Developer switches: select cross-check variants of the kernels (parity tests, A/B measurements); none changes a result.
+ * Names: monolithic_rt, no_prune, no_fuse, rt_legacy, no_root_rect, pool_small, split_depth, raster_inline_shade, mlaa_scan,
+ * mlaa_fullscan, mlaa_nobatch, no_frame_overlap, bvh_serial_split, pool_stats (csrc/cuda/rt_kernels.cuh `Switches` documents each).
+ * Defaults come from the environment variables B200R_<NAME IN CAPITALS>, read once by b200r_init. Waits for frames in flight. */
+int  b200r_set_switch(b200r_ctx* ctx, const char* name, int value);
 int  b200r_set_counters(b200r_ctx* ctx, int enabled);   /* counting costs time; off by default */
 int  b200r_get_counters(b200r_ctx* ctx, b200r_counters* out);
 /* Device time (ms, CUDA events on the launching stream) of the kernels of the last frame. */

@@ -6,6 +6,7 @@ reference's domain (Scene / Camera / Light / Screen and the Scene::render* entry
 reference src/Scene.h:76-85). There is no Python or CPU rendering fallback: if the library is
 missing, importing works but every use raises; if there is no B200, Renderer() raises.
 """
+import contextlib
 import ctypes as C
 import os
 
@@ -256,6 +257,19 @@ class Renderer:
             _check(lib().b200r_set_tile_profile(self._ctx, 0), self._ctx)
         return out
 
+    def set_switch(self, name, value=1):
+        """Developer switch (b200r_set_switch): selects a cross-check variant of a kernel; results never change."""
+        _check(lib().b200r_set_switch(self._ctx, name.encode(), int(value)), self._ctx)
+
+    @contextlib.contextmanager
+    def switch(self, name, value=1, restore=0):
+        """`with gpu.switch("no_prune"): ...` - the switch is set inside the block and put back to `restore` after it."""
+        self.set_switch(name, value)
+        try:
+            yield self
+        finally:
+            self.set_switch(name, restore)
+
     def set_counters(self, enabled):
         _check(lib().b200r_set_counters(self._ctx, 1 if enabled else 0), self._ctx)
 
@@ -290,8 +304,11 @@ class Renderer:
     def render_async(self, frame, out):
         """b200r_render_async: enqueue the frame; `out` (rows x width uint32, ideally page-locked) is complete after
         wait() or after the (pipeline depth + 1)-th following render_async()."""
-        self._pending = getattr(self, "_pending", [])[-getattr(self, "_depth", 2):] + [out]   # keep the in-flight buffers alive
+        pending = getattr(self, "_pending", []) + [out]
         _check(lib().b200r_render_async(self._ctx, C.byref(frame), out.ctypes.data), self._ctx)
+        # the call above retired the frame submitted depth+1 calls ago (its staging copy may land in that buffer during the call):
+        # only now may older buffers be let go; the last depth+1 are still in flight
+        self._pending = pending[-(getattr(self, "_depth", 2) + 1):]
         return out
 
     def wait(self):

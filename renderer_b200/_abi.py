@@ -83,7 +83,7 @@ SYMBOLS = {
     "b200r_selftest_mlaa_steps_host": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]),
     "b200r_set_tile_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "b200r_get_tile_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, P(C.c_uint32)]),
-    "b200r_get_warp_profile": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, P(C.c_uint32)]),
+    "b200r_set_switch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "b200r_set_counters": (C.c_int, [C.c_void_p, C.c_int]),
     "b200r_get_counters": (C.c_int, [C.c_void_p, P(Counters)]),
     "b200r_last_kernel_ms": (C.c_int, [C.c_void_p, P(C.c_float), P(C.c_float)]),

@@ -206,7 +206,7 @@ struct DevBuf {
 // Returns cudaSuccess and *depth = -1 - (levels) when the tree is deeper than maxDepth allows (caller reports it).
 cudaError_t launch_bvh_build(const float* h_vertPos, int strideFloats, uint32_t nVerts, const uint32_t* h_idx, uint32_t nTris,
                              void* h_nodes_out, uint32_t nodesCap, int32_t* h_order_out, uint32_t* nNodes, int32_t* depth,
-                             int maxLevels, cudaStream_t st, int& launches)
+                             int maxLevels, cudaStream_t st, int& launches, bool serialSplit)
 {
     DevBuf db;
     const size_t N = nTris, cap = 2 * N + 2;
@@ -233,7 +233,7 @@ cudaError_t launch_bvh_build(const float* h_vertPos, int strideFloats, uint32_t 
         if ((int)levelBegin.size() > maxLevels) { *depth = -1 - (int)levelBegin.size(); *nNodes = 0; return cudaGetLastError(); }
         const int n = end - begin;
         bvh_candidates_kernel<<<(unsigned)(n * 3 * CAND_CHUNKS), CAND_BLOCK, 0, st>>>(b, begin);
-        if (n <= 2048 && !getenv("B200R_BVH_SERIAL_SPLIT")) bvh_split_block_kernel<<<(unsigned)n, SPLIT_BLOCK, 0, st>>>(b, begin);       // few nodes, large segments: a CTA per node
+        if (n <= 2048 && !serialSplit) bvh_split_block_kernel<<<(unsigned)n, SPLIT_BLOCK, 0, st>>>(b, begin);       // few nodes, large segments: a CTA per node
         else bvh_split_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b, begin, end);
         launches += 2;
         int32_t pool = 0;

@@ -4,6 +4,7 @@
 // (reference src/renderer.cc:522-583). There is deliberately NO CPU rendering path in this library:
 // if CUDA is unavailable b200r_init() fails and nothing can be rendered.
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstddef>
 #include <cstdlib>
@@ -61,6 +62,7 @@ struct b200r_ctx {
     unsigned asyncIdx = 0;
     unsigned* d_tileCounter = nullptr;
     DeviceCounters* d_ctr = nullptr;
+    Switches sw{};                                              // developer switches (b200r_set_switch / environment at b200r_init)
     RasterBuffers rb{};
     WireBuffers wb{};
     size_t zkey_pixels = 0;
@@ -159,7 +161,7 @@ int mlaa_on(b200r_ctx* ctx, uint32_t* d_frame, uint32_t width, uint32_t height, 
     }
     int launches = 0;
     void* lines = nullptr;
-    if (!getenv("B200R_MLAA_SCAN")) {           // default: two-stage blending (all separation lines first, then the ordered blends)
+    if (!ctx->sw.mlaa_scan) {           // default: two-stage blending (all separation lines first, then the ordered blends)
         const size_t need = mlaa_lines_bytes((int)width, (int)height);
         if (ctx->mlaaLinesBytes < need) {
             if (ctx->d_mlaaLines) cudaFree(ctx->d_mlaaLines);
@@ -169,7 +171,7 @@ int mlaa_on(b200r_ctx* ctx, uint32_t* d_frame, uint32_t width, uint32_t height, 
         }
         lines = ctx->d_mlaaLines;
     }
-    CU(launch_mlaa(d_frame, ctx->d_mlaaScratch, (int)width, (int)height, ctx->numSMs, s, launches, lines));
+    CU(launch_mlaa(d_frame, ctx->d_mlaaScratch, (int)width, (int)height, ctx->numSMs, s, launches, lines, ctx->sw));
     ctx->last_launches += (uint32_t)launches;
     return B200R_OK;
 }
@@ -179,7 +181,7 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
     int rc = make_frame_params(ctx, f, fp);
     if (rc) return rc;
     if (!ctx->have_scene) return fail(ctx, B200R_ESTATE, "b200r_render before b200r_upload_scene");
-    if (ctx->counting) CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(DeviceCounters), stream));
+    if (ctx->counting || ctx->sw.pool_stats) CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(DeviceCounters), stream));
     ctx->last_launches = 0;
     CU(cudaEventRecord(ctx->ev0, stream));
     switch (fp.mode) {
@@ -203,44 +205,19 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
             RtBuffers& rt = ctx->rts[scratchSet];
             if (!ctx->tileCounters[scratchSet]) CU(cudaMalloc((void**)&ctx->tileCounters[scratchSet], 64));
             if (rt.pixels < px32) {
-                cudaFree(rt.queue); cudaFree(rt.hits); cudaFree(rt.keys); cudaFree(rt.pend);
-                rt.queue = nullptr; rt.hits = nullptr; rt.keys = nullptr; rt.pend = nullptr; rt.pixels = 0;
-                CU(cudaMalloc((void**)&rt.queue, px32 * 8 * 8));        // <= 8 jobs of 8 bytes per pixel
-                CU(cudaMalloc((void**)&rt.hits, px32 * 32));
-                CU(cudaMalloc((void**)&rt.keys, px32 * 8));
-                cudaFree(rt.srays); cudaFree(rt.sword); cudaFree(rt.queue2);
-                rt.srays = nullptr; rt.sword = nullptr; rt.queue2 = nullptr;
-                CU(cudaMalloc((void**)&rt.srays, px32 * 48));
-                CU(cudaMalloc((void**)&rt.sword, px32 * 4));
-                cudaFree(rt.sdon); rt.sdon = nullptr;
-                CU(cudaMalloc((void**)&rt.sdon, px32 * 4));
-                CU(cudaMemsetAsync(rt.sdon, 0, px32 * 4, stream));
-                CU(cudaMalloc((void**)&rt.queue2, px32 * 8 * 8));
-                CU(cudaMalloc((void**)&rt.pend, px32 * 4));
+                cudaFree(rt.hits); rt.hits = nullptr; rt.pixels = 0;
+                CU(cudaMalloc((void**)&rt.hits, px32 * 32));             // one 32-byte hit record per pixel at most
                 rt.pixels = px32;
             }
-            rt.counters = ctx->tileCounters[scratchSet];
-            rt.forceMonolithic = getenv("B200R_MONOLITHIC_RT") != nullptr;
-            rt.noPrune = getenv("B200R_NO_PRUNE") != nullptr;
-            {
-                const char* pth = getenv("B200R_RT_PATH");       // generic | fused (default) | jobs
-                rt.fuseMode = (getenv("B200R_NO_FUSE") || (pth && !strcmp(pth, "generic"))) ? 0 : ((pth && !strcmp(pth, "jobs")) ? 2 : 1);
+            if ((ctx->counting || ctx->sw.rt_legacy) && rt.legacyPixels < px32) {      // job pipeline: counting / legacy runs only
+                cudaFree(rt.queue); cudaFree(rt.keys); rt.queue = nullptr; rt.keys = nullptr; rt.legacyPixels = 0;
+                CU(cudaMalloc((void**)&rt.queue, px32 * 8 * 8));        // <= 8 jobs of 8 bytes per pixel
+                CU(cudaMalloc((void**)&rt.keys, px32 * 8));
+                rt.legacyPixels = px32;
             }
-            rt.refillBelow = getenv("B200R_REFILL_BELOW") ? atoi(getenv("B200R_REFILL_BELOW")) : 0;
-            rt.noRootCull = getenv("B200R_NO_ROOT_RECT") != nullptr;
-            rt.sched = (getenv("B200R_RT_SCHED") && !strcmp(getenv("B200R_RT_SCHED"), "wave")) ? 1 : 0;
-            rt.lateWeight = getenv("B200R_LATE_WEIGHT") ? atoi(getenv("B200R_LATE_WEIGHT")) : 0;
-            rt.prefetchCur = getenv("B200R_NO_PREFETCH_CUR") ? 0 : 1;
-            rt.longT = getenv("B200R_LONG_T") ? atoi(getenv("B200R_LONG_T")) : 0;
-            rt.splitDepth = getenv("B200R_SPLIT_DEPTH") ? atoi(getenv("B200R_SPLIT_DEPTH")) : -1;
-            rt.blocksPerSM = getenv("B200R_BLOCKS_PER_SM") ? atoi(getenv("B200R_BLOCKS_PER_SM")) : 0;
-            rt.innerBurst = getenv("B200R_INNER_BURST") ? atoi(getenv("B200R_INNER_BURST")) : 0;
-            if (getenv("B200R_WARP_PROFILE")) {
-                if (!rt.warpProf) CU(cudaMalloc((void**)&rt.warpProf, (size_t)65536 * 32));
-                prof = nullptr;
-            } else if (rt.warpProf) { cudaFree(rt.warpProf); rt.warpProf = nullptr; }
+            rt.counters = ctx->tileCounters[scratchSet];
             int launches = 0;
-            CU(launch_raytrace(ctx->sc, fp, d_out, rt, ctx->d_ctr, ctx->counting, prof, ctx->numSMs, stream, launches));
+            CU(launch_raytrace(ctx->sc, fp, d_out, rt, ctx->sw, ctx->d_ctr, ctx->counting, prof, ctx->numSMs, stream, launches));
             ctx->last_launches += (uint32_t)launches;
         }
         break;
@@ -262,7 +239,7 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
             CU(cudaMalloc((void**)&ctx->rb.zkeys, px * 8));
             ctx->zkey_pixels = px;
         }
-        if (fp.mode >= B200R_MODE_PHONG && !getenv("B200R_RASTER_INLINE_SHADE")) {      // per-pixel lighting pass (default)
+        if (fp.mode >= B200R_MODE_PHONG && !ctx->sw.raster_inline_shade) {      // per-pixel lighting pass (default)
             if (ctx->attr_pixels < px) {
                 if (ctx->d_attrs) cudaFree(ctx->d_attrs);
                 ctx->d_attrs = nullptr; ctx->attr_pixels = 0;
@@ -341,7 +318,30 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
 
 }  // namespace
 
+struct SwitchName { const char* name; int Switches::*field; };
+const SwitchName kSwitches[] = {
+    {"monolithic_rt", &Switches::monolithic_rt}, {"no_prune", &Switches::no_prune}, {"no_fuse", &Switches::no_fuse},
+    {"rt_legacy", &Switches::rt_legacy}, {"no_root_rect", &Switches::no_root_rect}, {"pool_small", &Switches::pool_small},
+    {"split_depth", &Switches::split_depth}, {"raster_inline_shade", &Switches::raster_inline_shade}, {"mlaa_scan", &Switches::mlaa_scan},
+    {"mlaa_fullscan", &Switches::mlaa_fullscan}, {"mlaa_nobatch", &Switches::mlaa_nobatch},
+    {"no_frame_overlap", &Switches::no_frame_overlap}, {"bvh_serial_split", &Switches::bvh_serial_split},
+    {"pool_stats", &Switches::pool_stats},
+};
+
 extern "C" {
+
+int b200r_set_switch(b200r_ctx* ctx, const char* name, int value)
+{
+    if (!ctx || !name) return fail(ctx, B200R_EINVAL, "b200r_set_switch: NULL argument");
+    for (const SwitchName& n : kSwitches)
+        if (!strcmp(n.name, name)) {
+            int rc = b200r_wait(ctx);               // frames in flight were enqueued under the old setting
+            if (rc) return rc;
+            ctx->sw.*(n.field) = value;
+            return B200R_OK;
+        }
+    return fail(ctx, B200R_EINVAL, std::string("b200r_set_switch: unknown switch '") + name + "'");
+}
 
 const char* b200r_last_error(const b200r_ctx* ctx) { return ctx ? ctx->err.c_str() : global_error(); }
 
@@ -373,6 +373,12 @@ int b200r_init(int device, b200r_ctx** out)
     CU(cudaMemset(ctx->d_ctr, 0, sizeof(DeviceCounters)));
     CU(cudaMalloc((void**)&ctx->rb.spanCount, 64));
     CU(cudaMallocHost((void**)&ctx->h_spanCount, 64));
+    CU(rt_pool_configure());
+    for (const SwitchName& n : kSwitches) {      // defaults from the environment, read ONCE here - never on the per-frame path
+        std::string env = "B200R_";
+        for (const char* c = n.name; *c; c++) env += (char)toupper((unsigned char)*c);
+        if (const char* v = getenv(env.c_str())) ctx->sw.*(n.field) = (*v >= '0' && *v <= '9') || *v == '-' ? atoi(v) : 1;
+    }
     *out = ctx;
     return B200R_OK;
 }
@@ -387,8 +393,7 @@ void b200r_destroy(b200r_ctx* ctx)
     cudaFree(ctx->wb.counts); cudaFree(ctx->wb.offsets); cudaFree(ctx->wb.blockSums); cudaFree(ctx->wb.total); cudaFree(ctx->wb.frags);
     for (int k = 0; k < B200R_MAX_FRAMES_IN_FLIGHT; k++) {
         RtBuffers& rt = ctx->rts[k];
-        cudaFree(rt.queue); cudaFree(rt.hits); cudaFree(rt.keys); cudaFree(rt.pend);
-        cudaFree(rt.srays); cudaFree(rt.sword); cudaFree(rt.queue2); cudaFree(rt.warpProf); cudaFree(rt.sdon);
+        cudaFree(rt.queue); cudaFree(rt.hits); cudaFree(rt.keys);
         if (k) cudaFree(ctx->tileCounters[k]);
         if (ctx->rstream[k]) cudaStreamDestroy(ctx->rstream[k]);
     }
@@ -415,7 +420,7 @@ int b200r_upload_scene(b200r_ctx* ctx, const b200r_vertex* verts, uint32_t n_ver
 {
     if (!ctx) return fail(nullptr, B200R_EINVAL, "NULL ctx");
     if (!verts || !tris || n_verts == 0 || n_tris == 0) return fail(ctx, B200R_EINVAL, "empty scene");
-    if ((nodes == nullptr) != (tri_idx == nullptr && n_tri_idx == 0) && nodes == nullptr)
+    if ((nodes != nullptr && n_nodes != 0) != (tri_idx != nullptr && n_tri_idx != 0))
         return fail(ctx, B200R_EINVAL, "nodes and tri_idx must be given together");
     CU(cudaSetDevice(ctx->device));
     for (uint32_t i = 0; i < n_tris; i++)
@@ -424,6 +429,14 @@ int b200r_upload_scene(b200r_ctx* ctx, const b200r_vertex* verts, uint32_t n_ver
 
     // ---- validate the BVH like CreateCFBVH does (depth < stack size), plus index ranges
     if (nodes && n_nodes) {
+        // every node, reachable or not: the re-layout below walks all of them
+        for (uint32_t i = 0; i < n_nodes; i++) {
+            if (nodes[i].a & 0x80000000u) {
+                if ((uint64_t)nodes[i].b + (nodes[i].a & 0x7fffffffu) > n_tri_idx)
+                    return fail(ctx, B200R_EINVAL, "BVH leaf range outside the triangle index list");
+            } else if (nodes[i].a >= n_nodes || nodes[i].b >= n_nodes)
+                return fail(ctx, B200R_EINVAL, "BVH child index out of range");
+        }
         std::vector<std::pair<uint32_t, int>> st; st.push_back({0u, 0});
         size_t visited = 0;
         while (!st.empty()) {
@@ -445,7 +458,12 @@ int b200r_upload_scene(b200r_ctx* ctx, const b200r_vertex* verts, uint32_t n_ver
     // rest of the tree is pruned as usual.
     std::vector<unsigned char> bad_tri(n_tris, 0);
     b200r::count_unbounded_triangles(verts, n_verts, tris, n_tris, 2e-5, bad_tri.data());
-    const uint32_t prune_ok = 1;
+    // The pruning slack (1e-4 box margin, hits within ~3e-6 of their triangle) is an ABSOLUTE error budget: it covers the fp32
+    // rounding of hit = o + d*s only while coordinates stay small. The loader rescales every model to |coord| <= 1.2; geometry
+    // handed in directly at another scale is traversed without pruning (identical results, more work).
+    uint32_t prune_ok = 1;
+    for (uint32_t i = 0; i < n_verts && prune_ok; i++)
+        for (int c = 0; c < 3; c++) if (!(fabsf(verts[i].pos[c]) <= 8.0f)) prune_ok = 0;
 
     std::vector<float4> hn, hl, hs, hv, ht;
     uint32_t root_ref = 0xFFFFFFFFu, fast_ok = 1;
@@ -479,14 +497,35 @@ int b200r_upload_scene(b200r_ctx* ctx, const b200r_vertex* verts, uint32_t n_ver
         // so one reverse sweep is a post-order pass
         {
             std::vector<unsigned char> sub(n_nodes, 0);
+            std::vector<float> tlo(3 * (size_t)n_nodes), thi(3 * (size_t)n_nodes);
             for (uint32_t ii = n_nodes; ii-- > 0;) {
+                // tlo/thi: actual bounds of the triangles below the node. Pruning assumes they lie inside the node's box
+                // (the reference's builder guarantees it, a caller's own tree may not): if not, the subtree is never pruned.
                 if (nodes[ii].a & 0x80000000u) {
                     const uint32_t cnt = nodes[ii].a & 0x7fffffffu;
-                    for (uint32_t k = 0; k < cnt; k++) if (bad_tri[(uint32_t)tri_idx[nodes[ii].b + k]]) sub[ii] = 1;
+                    for (int c = 0; c < 3; c++) { tlo[3 * (size_t)ii + c] = FLT_MAX; thi[3 * (size_t)ii + c] = -FLT_MAX; }
+                    for (uint32_t k = 0; k < cnt; k++) {
+                        const uint32_t ti = (uint32_t)tri_idx[nodes[ii].b + k];
+                        if (bad_tri[ti]) sub[ii] = 1;
+                        const uint32_t vi[3] = {tris[ti].a, tris[ti].b, tris[ti].c};
+                        for (int v = 0; v < 3; v++)
+                            for (int c = 0; c < 3; c++) {
+                                const float x = verts[vi[v]].pos[c];
+                                if (!(x >= tlo[3 * (size_t)ii + c])) tlo[3 * (size_t)ii + c] = x;      // NaN propagates into the bounds
+                                if (!(x <= thi[3 * (size_t)ii + c])) thi[3 * (size_t)ii + c] = x;
+                            }
+                    }
+                    if (cnt == 0) for (int c = 0; c < 3; c++) { tlo[3 * (size_t)ii + c] = nodes[ii].lo[c]; thi[3 * (size_t)ii + c] = nodes[ii].hi[c]; }
                 } else {
                     if (nodes[ii].a <= ii || nodes[ii].b <= ii) { std::fill(sub.begin(), sub.end(), 1); break; }   // not pre-order: be safe
                     sub[ii] = sub[nodes[ii].a] | sub[nodes[ii].b];
+                    for (int c = 0; c < 3; c++) {
+                        tlo[3 * (size_t)ii + c] = fminf(tlo[3 * (size_t)nodes[ii].a + c], tlo[3 * (size_t)nodes[ii].b + c]);
+                        thi[3 * (size_t)ii + c] = fmaxf(thi[3 * (size_t)nodes[ii].a + c], thi[3 * (size_t)nodes[ii].b + c]);
+                    }
                 }
+                for (int c = 0; c < 3; c++)
+                    if (!(tlo[3 * (size_t)ii + c] >= nodes[ii].lo[c] - 1e-5f && thi[3 * (size_t)ii + c] <= nodes[ii].hi[c] + 1e-5f)) sub[ii] = 1;
             }
             for (uint32_t ii = 0; ii < n_nodes; ii++) {
                 if (nodes[ii].a & 0x80000000u) continue;
@@ -709,7 +748,7 @@ int b200r_render_async(b200r_ctx* ctx, const b200r_frame* f, uint32_t* host_xrgb
     // are still being walked (the persistent kernel's CTAs retire one by one) and takes over the SMs they free.
     // Everything else (and any profiling / counting run) stays on the one stream and is therefore serialised.
     const bool overlap = (fp.mode == B200R_MODE_RAYTRACE || fp.mode == B200R_MODE_RAYTRACE_AA) && !ctx->counting && !ctx->tileProfile &&
-                         !getenv("B200R_WARP_PROFILE") && !getenv("B200R_NO_FRAME_OVERLAP") && !(f->flags & B200R_F_MLAA);
+                         !ctx->sw.no_frame_overlap && !(f->flags & B200R_F_MLAA);
     const int set = overlap ? (int)(ctx->asyncIdx % ctx->depth) : 0;
     if (set && !ctx->rstream[set]) CU(cudaStreamCreateWithFlags(&ctx->rstream[set], cudaStreamNonBlocking));
     cudaStream_t rs = set ? ctx->rstream[set] : ctx->stream;
@@ -774,7 +813,7 @@ int b200r_build_bvh(b200r_ctx* ctx, const b200r_vertex* verts, uint32_t n_verts,
     int launches = 0;
     // levels <= BVH_STACK_SIZE: the reference refuses deeper trees (Raytracer.cc:711-717)
     CU(launch_bvh_build(verts[0].pos, (int)(sizeof(b200r_vertex) / sizeof(float)), n_verts, idx.data(), n_tris, nodes_out, nodes_cap,
-                        tri_idx_out, n_nodes, depth, B200R_BVH_STACK_SIZE, ctx->stream, launches));
+                        tri_idx_out, n_nodes, depth, B200R_BVH_STACK_SIZE, ctx->stream, launches, ctx->sw.bvh_serial_split != 0));
     ctx->last_launches = (uint32_t)launches;
     if (*depth < 0) return fail(ctx, B200R_EDEPTH, "Max depth of BVH exceeds BVH_STACK_SIZE");
     return B200R_OK;
@@ -808,31 +847,11 @@ int b200r_set_tile_profile(b200r_ctx* ctx, int enabled)
 int b200r_get_tile_profile(b200r_ctx* ctx, uint64_t* start_end_ns, uint32_t max_tiles, uint32_t* n_tiles)
 {
     if (!ctx || !n_tiles) return fail(ctx, B200R_EINVAL, "NULL argument");
-    if (ctx->rts[0].warpProf) {      // B200R_WARP_PROFILE: per-warp records of rt_primary_kernel (2 "tiles" per warp)
-        *n_tiles = getenv("B200R_JOB_PROFILE") ? 131072u : ctx->rts[0].lastPrimaryWarps * 2;     // whole buffer incl. job statistics
-        if (!start_end_ns) return B200R_OK;
-        CU(cudaSetDevice(ctx->device));
-        const uint32_t n = *n_tiles < max_tiles ? *n_tiles : max_tiles;
-        CU(cudaMemcpy(start_end_ns, ctx->rts[0].warpProf, (size_t)n * 16, cudaMemcpyDeviceToHost));
-        return B200R_OK;
-    }
     *n_tiles = ctx->lastTiles;
     if (!start_end_ns || !ctx->d_tileProf) return B200R_OK;
     CU(cudaSetDevice(ctx->device));
     const uint32_t n = ctx->lastTiles < max_tiles ? ctx->lastTiles : max_tiles;
     CU(cudaMemcpy(start_end_ns, ctx->d_tileProf, (size_t)n * 16, cudaMemcpyDeviceToHost));
-    return B200R_OK;
-}
-
-int b200r_get_warp_profile(b200r_ctx* ctx, uint32_t scratch_slot, uint64_t* records, uint32_t max_warps, uint32_t* n_warps)
-{
-    if (!ctx || !n_warps || scratch_slot >= B200R_MAX_FRAMES_IN_FLIGHT) return fail(ctx, B200R_EINVAL, "b200r_get_warp_profile: bad argument");
-    const RtBuffers& rt = ctx->rts[scratch_slot];
-    *n_warps = rt.warpProf ? rt.lastPrimaryWarps : 0u;
-    if (!records || !rt.warpProf) return B200R_OK;
-    CU(cudaSetDevice(ctx->device));
-    const uint32_t n = *n_warps < max_warps ? *n_warps : max_warps;
-    CU(cudaMemcpy(records, rt.warpProf, (size_t)n * 32, cudaMemcpyDeviceToHost));      // synchronises with the device
     return B200R_OK;
 }
 

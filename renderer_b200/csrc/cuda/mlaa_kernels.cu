@@ -252,7 +252,7 @@ size_t mlaa_lines_bytes(int resX, int resY)
 }
 
 cudaError_t launch_mlaa(uint32_t* d_frame, uint32_t* d_scratch, int resX, int resY, int numSMs, cudaStream_t st, int& launches,
-                        void* d_lines)
+                        void* d_lines, const Switches& sw)
 {
     mlaa_find_fragments_kernel<<<numSMs * 4, 256, 0, st>>>(d_frame, d_scratch, resX, resY);
     const int n_hscan_jobs = (resY / 8) + ((resY % 8) ? 1 : 0);
@@ -269,8 +269,8 @@ cudaError_t launch_mlaa(uint32_t* d_frame, uint32_t* d_scratch, int resX, int re
         int* listCount = endV + resX; int* list = listCount + 4;
         mlaa_lines_reset_kernel<<<(resX + resY + 255) / 256, 256, 0, st>>>(cntH, endH, resX + resY, listCount);   // cntH|cntV and endH|endV are contiguous
         // batched flag / pixel loads need runs shorter than a row/column by a wide margin (mlaa_steps.h); tiny frames walk step by step
-        const bool batch = resX >= 4 * BLEND_BATCH && resY >= 4 * BLEND_BATCH && !getenv("B200R_MLAA_NOBATCH");
-        const bool fullScan = getenv("B200R_MLAA_FULLSCAN") != nullptr;
+        const bool batch = resX >= 4 * BLEND_BATCH && resY >= 4 * BLEND_BATCH && !sw.mlaa_nobatch;
+        const bool fullScan = sw.mlaa_fullscan != 0;
         if (fullScan) mlaa_lines_kernel<<<numSMs * 8, 256, 0, st>>>(d_scratch, resX, resY, recH, recV, cntH, cntV, endH, endV, capH, capV);
         else {
             mlaa_line_starts_kernel<<<numSMs * 8, 256, 0, st>>>(d_scratch, resX, resY, list, listCount);

@@ -4,30 +4,37 @@
 
 namespace b200r {
 
-// Scratch of the ray tracer: `counters` = {tile counter / queue head, root-survivor count, hit count, spare};
-// `queue` = (pixel, subtree) jobs of the primary rays that enter the root box (<= 8 per pixel); `hits` = 32-byte hit
-// records; `keys`/`pend` = per pixel: best (hitZ, list position) so far and number of jobs still running.
+// Developer switches (b200r_set_switch; defaults from the environment variables B200R_<NAME>, read ONCE at b200r_init).
+// They select cross-check variants of the kernels for the parity tests and A/B measurements; none changes a result.
+struct Switches {
+    int monolithic_rt = 0;        // rt_frame_kernel for every ray-traced frame
+    int no_prune = 0;             // no distance pruning in the closest-hit traversal
+    int no_fuse = 0;              // simple configuration through hit records + rt_shade_kernel as well
+    int rt_legacy = 0;            // round 1's job pipeline (rt_rootcull_kernel + rt_primary_kernel) instead of rt_pool_kernel
+    int no_root_rect = 0;         // no screen rectangle around the root box: every pixel's ray is built
+    int pool_small = 0;           // 128-entry pools: exercises the overflow guard of rt_pool_kernel
+    int split_depth = -1;         // job pipeline: BVH levels expanded into jobs (0..3; default 2)
+    int raster_inline_shade = 0;  // modes 6-8 shade inside the span walk instead of the per-pixel pass
+    int mlaa_scan = 0;            // row-scanning MLAA kernels instead of the two-stage path
+    int mlaa_fullscan = 0;        // two-stage MLAA, lines walked by the scanning thread
+    int mlaa_nobatch = 0;         // MLAA walks load one word per step
+    int no_frame_overlap = 0;     // b200r_render_async keeps ray-traced frames on one stream
+    int bvh_serial_split = 0;     // BVH build: one thread per node in every level
+    int pool_stats = 0;           // rt_pool_kernel adds its per-phase iteration / lane counts to the work counters (tools/pool_stats.py)
+};
+
+// Scratch of the ray tracer: `counters` = {tile counter / job queue head, job count, hit count, pixel counter of the pooled kernel};
+// `hits` = 32-byte hit records (generic configurations: one per pixel at most). `queue` ((pixel, subtree) jobs, <= 8 per pixel) and
+// `keys` (per-pixel merge words) belong to the job pipeline and are only allocated for counting / legacy runs.
 struct RtBuffers {
     unsigned* counters = nullptr;
-    void* queue = nullptr;
-    unsigned long long* keys = nullptr;
-    unsigned* pend = nullptr;
     void* hits = nullptr;
     size_t pixels = 0;
-    bool forceMonolithic = false;
-    bool noPrune = false;
-    int fuseMode = 1;                          // simple config (1 light, no reflections/AO): 0 generic shade kernel, 1 fused lanes, 2 shadow jobs
-    bool noRootCull = false;                   // B200R_NO_ROOT_RECT: K0 builds every pixel's ray (no screen rectangle)
-    unsigned* sdon = nullptr;                  // fused path: merge words of shadow rays split over lanes (all zero between frames)
-    void* srays = nullptr; unsigned* sword = nullptr; void* queue2 = nullptr;   // shadow-job pipeline: ray records (48 B), merge words, jobs
-    int refillBelow = 0, innerBurst = 0;      // tuning overrides (B200R_REFILL_BELOW / B200R_INNER_BURST), 0 = built-in
-    int sched = 0;                             // 0: rt_primary_kernel (rounds, default); 1: rt_wave_kernel (state-voting scheduler, measured slower) - B200R_RT_SCHED=wave
-    int lateWeight = 0, prefetchCur = 1, longT = 0;   // rt_wave_kernel tuning (B200R_LATE_WEIGHT / B200R_NO_PREFETCH_CUR / B200R_LONG_T)
-    int splitDepth = -1, blocksPerSM = 0;       // B200R_SPLIT_DEPTH (0..3, default 2) / B200R_BLOCKS_PER_SM (cap on resident CTAs of the persistent kernel)
-    unsigned long long* warpProf = nullptr;   // developer tool (B200R_WARP_PROFILE): 4 x u64 per warp of rt_primary_kernel
-    unsigned lastPrimaryWarps = 0;
+    void* queue = nullptr;
+    unsigned long long* keys = nullptr;
+    size_t legacyPixels = 0;
 };
-cudaError_t launch_raytrace(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, RtBuffers& rt,
+cudaError_t launch_raytrace(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, RtBuffers& rt, const Switches& sw,
                             DeviceCounters* d_ctr, bool count, unsigned long long* d_tileProf, int numSMs, cudaStream_t stream,
                             int& launches);
 
@@ -53,13 +60,19 @@ cudaError_t launch_wire_emit(const DeviceScene& sc, const FrameParams& fp, uint3
                              int& launches);
 // d_lines: mlaa_lines_bytes(resX, resY) bytes of scratch for the two-stage path (line records per row); nullptr = row-scanning kernels
 cudaError_t launch_mlaa(uint32_t* d_frame, uint32_t* d_scratch, int resX, int resY, int numSMs, cudaStream_t st, int& launches,
-                        void* d_lines);
+                        void* d_lines, const Switches& sw);
 size_t mlaa_lines_bytes(int resX, int resY);
 // SAH BVH build on the device (bvh_build.cu): host arrays in (vertex positions with a float stride, 3 indices per triangle), the
 // flattened tree out (32-byte nodes in DFS pre-order + the triangle index list). *depth < 0: deeper than maxLevels - 1.
 cudaError_t launch_bvh_build(const float* h_vertPos, int strideFloats, uint32_t nVerts, const uint32_t* h_idx, uint32_t nTris,
                              void* h_nodes_out, uint32_t nodesCap, int32_t* h_order_out, uint32_t* nNodes, int32_t* depth,
-                             int maxLevels, cudaStream_t st, int& launches);
+                             int maxLevels, cudaStream_t st, int& launches, bool serialSplit);
+// rt_pool.cu: the pooled traversal kernel (clears the frame, then writes lit pixels / hit records)
+bool pool_supported(const DeviceScene& sc);
+cudaError_t rt_pool_configure();            // once per device: opt in to > 48 KB of dynamic shared memory
+cudaError_t launch_rt_pool(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, bool fused, bool prune, bool smallCap,
+                           bool noRootRect, unsigned* pixelCounter, void* hits, unsigned* hitCount, int numSMs, cudaStream_t stream,
+                           int& launches, DeviceCounters* stats = nullptr);
 cudaError_t launch_division_selftest(unsigned long long samples, uint32_t seed, unsigned long long* d_mismatches,
                                      float* d_firstBad, int numSMs, cudaStream_t stream);
 cudaError_t launch_deinterleave(const uint32_t* gathered, uint32_t* frame, uint32_t W, uint32_t H, uint32_t P,

@@ -24,7 +24,7 @@ def test_mlaa_vs_reference_golden(rb, load_scene, gpu, name):
 
 @pytest.mark.parametrize("model,mode,size", [("statue.ply", 6, (800, 600)), ("chessboard.tri", 9, (640, 480)),
                                              ("statue.ply", 5, (3840, 2160)), ("chessboard.tri", 6, (1920, 1080))])
-def test_mlaa_vs_oracle(rb, pyport, load_scene, gpu, monkeypatch, model, mode, size):
+def test_mlaa_vs_oracle(rb, pyport, load_scene, gpu, model, mode, size):
     s = load_scene(model, bvh=mode >= 9)
     gpu.upload(s)
     cam = rb.Orbit.cameras([9])[9]
@@ -32,17 +32,14 @@ def test_mlaa_vs_oracle(rb, pyport, load_scene, gpu, monkeypatch, model, mode, s
     got = gpu.render(f)                                  # default: two-stage blending (all lines first, then the ordered blends)
     want = pyport.render(s, f)
     assert_parity(got, want, f"{model} mode {mode} {size} + MLAA")
-    monkeypatch.setenv("B200R_MLAA_SCAN", "1")
-    scan = gpu.render(f)                                 # row-scanning kernels: lines found inside the ordered loop
-    monkeypatch.delenv("B200R_MLAA_SCAN")
+    with gpu.switch("mlaa_scan"):
+        scan = gpu.render(f)                             # row-scanning kernels: lines found inside the ordered loop
     assert np.array_equal(got, scan)
-    monkeypatch.setenv("B200R_MLAA_FULLSCAN", "1")
-    full = gpu.render(f)                                 # two-stage, but the scanning thread also walks the line it finds
-    monkeypatch.delenv("B200R_MLAA_FULLSCAN")
+    with gpu.switch("mlaa_fullscan"):
+        full = gpu.render(f)                             # two-stage, but the scanning thread also walks the line it finds
     assert np.array_equal(got, full)
-    monkeypatch.setenv("B200R_MLAA_NOBATCH", "1")
-    stepwise = gpu.render(f)                             # flag / pixel words loaded one step at a time, as the reference's loops do
-    monkeypatch.delenv("B200R_MLAA_NOBATCH")
+    with gpu.switch("mlaa_nobatch"):
+        stepwise = gpu.render(f)                         # flag / pixel words loaded one step at a time, as the reference's loops do
     assert np.array_equal(got, stepwise)
     plain = gpu.render(rb.make_frame(mode, size[0], size[1], cam))
     assert 0 < int((plain != got).sum()) < 0.2 * got.size       # the filter touches edges only

@@ -75,7 +75,7 @@ def test_row_sharding_matches_full_frame(rb, load_scene, gpu):
         assert np.array_equal(part, full[r::P])
 
 
-def test_split_pipeline_equals_monolithic_kernel(rb, load_scene, gpu, monkeypatch):
+def test_split_pipeline_equals_monolithic_kernel(rb, load_scene, gpu):
     """Mode 9 runs as root-cull -> persistent primary traversal -> shade; the single persistent kernel (used for
     mode 0) must give the same frame and the same work counters."""
     import numpy as np
@@ -86,8 +86,8 @@ def test_split_pipeline_equals_monolithic_kernel(rb, load_scene, gpu, monkeypatc
     gpu.set_counters(True)
     try:
         a = gpu.render(f); ca = gpu.counters()
-        monkeypatch.setenv("B200R_MONOLITHIC_RT", "1")
-        b = gpu.render(f); cb = gpu.counters()
+        with gpu.switch("monolithic_rt"):
+            b = gpu.render(f); cb = gpu.counters()
     finally:
         gpu.set_counters(False)
     assert np.array_equal(a, b)
@@ -96,7 +96,7 @@ def test_split_pipeline_equals_monolithic_kernel(rb, load_scene, gpu, monkeypatc
 
 @pytest.mark.parametrize("model,size", [("chessboard.tri", (1920, 1080)), ("dragon_vis.ply", (1280, 720)), ("tie.ply", (1280, 720)),
                                         ("x-wing.ply", (800, 600)), ("kerolamp.ply", (800, 600))])
-def test_distance_pruning_changes_nothing(rb, pyport, load_scene, gpu, monkeypatch, model, size):
+def test_distance_pruning_changes_nothing(rb, pyport, load_scene, gpu, model, size):
     """Near-first ordering + conservative distance pruning of the primary-ray kernel vs the reference's full traversal:
     same frame, on scenes that do (chessboard, tie, x-wing, kerolamp) and do not contain triangles flagged unprunable."""
     import numpy as np
@@ -105,9 +105,8 @@ def test_distance_pruning_changes_nothing(rb, pyport, load_scene, gpu, monkeypat
     for k, cam in rb.Orbit.cameras([0, 57]).items():
         f = rb.make_frame(rb.MODE_RAYTRACE, size[0], size[1], cam)
         pruned = gpu.render(f)
-        monkeypatch.setenv("B200R_NO_PRUNE", "1")
-        plain = gpu.render(f)
-        monkeypatch.delenv("B200R_NO_PRUNE")
+        with gpu.switch("no_prune"):
+            plain = gpu.render(f)
         assert np.array_equal(pruned, plain), f"{model} frame {k}"
         if k == 0:
             assert_parity(pruned, pyport.render(s, f), f"{model} {size} frame {k}")
@@ -115,52 +114,48 @@ def test_distance_pruning_changes_nothing(rb, pyport, load_scene, gpu, monkeypat
 
 @pytest.mark.parametrize("flags", [1 | 4, 4, 1, 0])
 @pytest.mark.parametrize("model", ["chessboard.tri", "dragon_vis.ply", "trainColor.tri"])
-def test_fused_shadow_continuation_equals_split_pipeline(rb, pyport, load_scene, gpu, monkeypatch, model, flags):
-    """One light, no reflections, no AO: primary lanes shade their hit and continue as its shadow ray (no hit queue, no
-    shade kernel). Must equal the split pipeline and the oracle."""
+def test_fused_shadow_continuation_equals_hit_record_path(rb, pyport, load_scene, gpu, model, flags):
+    """One light, no reflections, no AO: rt_pool_kernel shades a resolved hit itself and re-arms the slot as the hit's shadow ray.
+    Must equal the generic route (hit records + rt_shade_kernel), round 1's job pipeline, and the oracle."""
     import numpy as np
     s = load_scene(model)
     gpu.upload(s)
     cam = rb.Orbit.cameras([33])[33]
     f = rb.make_frame(rb.MODE_RAYTRACE, 1280, 720, cam, flags=flags)
-    fused = gpu.render(f)                                  # default: primary lanes continue as their shadow ray
-    monkeypatch.setenv("B200R_RT_PATH", "jobs")
-    jobs = gpu.render(f)                                   # shadow rays as (ray, subtree) jobs in a second persistent kernel
-    monkeypatch.setenv("B200R_RT_PATH", "generic")
-    split = gpu.render(f)                                  # generic shade kernel
-    monkeypatch.delenv("B200R_RT_PATH")
-    assert np.array_equal(jobs, split) and np.array_equal(fused, split)
-    assert_parity(jobs, pyport.render(s, f), f"{model} flags={flags} shadow-job pipeline")
+    fused = gpu.render(f)
+    with gpu.switch("no_fuse"):
+        split = gpu.render(f)
+    with gpu.switch("rt_legacy"):
+        legacy = gpu.render(f)
+    assert np.array_equal(fused, split) and np.array_equal(legacy, split)
+    assert_parity(fused, pyport.render(s, f), f"{model} flags={flags} fused shadow rays")
 
 
 @pytest.mark.parametrize("flags", [1 | 4, 1 | 2 | 4, 4])
 @pytest.mark.parametrize("model,size", [("chessboard.tri", (1920, 1080)), ("dragon_vis.ply", (1280, 720)), ("single.ply", (320, 240)),
-                                        ("trainColor.tri", (800, 600))])
-def test_state_voting_scheduler_equals_round_scheduler(rb, pyport, load_scene, gpu, monkeypatch, model, size, flags):
-    """rt_wave_kernel (one phase per warp iteration, chosen by vote; experimental) against rt_primary_kernel (all phases
-    every round; the default): same jobs, same merges - the frames must be identical, fused and generic paths, and equal the
-    oracle."""
+                                        ("trainColor.tri", (800, 600)), ("torus.ply", (640, 480))])
+def test_pool_overflow_guard_and_legacy_pipeline_agree(rb, pyport, load_scene, gpu, model, size, flags):
+    """rt_pool_kernel with 128-entry pools (the overflow guard - lanes walking whole subtrees with a private stack - runs all
+    the time) and round 1's lane-per-job pipeline against the default 512-entry pools: identical frames, fused and generic
+    configurations, and equal to the oracle."""
     import numpy as np
     s = load_scene(model)
     gpu.upload(s)
     for k, cam in rb.Orbit.cameras([3, 64]).items():
         f = rb.make_frame(rb.MODE_RAYTRACE, size[0], size[1], cam, flags=flags)
-        rounds = gpu.render(f)
-        monkeypatch.setenv("B200R_RT_SCHED", "wave")
-        wave = gpu.render(f)
-        assert np.array_equal(wave, rounds), f"{model} frame {k} flags={flags}"
-        for rf in (1, 32):                                  # refill thresholds at both extremes
-            monkeypatch.setenv("B200R_REFILL_BELOW", str(rf))
-            again = gpu.render(f)
-            monkeypatch.delenv("B200R_REFILL_BELOW")
-            assert np.array_equal(wave, again), f"{model} frame {k} flags={flags} refillMin={rf}"
-        monkeypatch.delenv("B200R_RT_SCHED")
+        pool = gpu.render(f)
+        with gpu.switch("pool_small"):
+            small = gpu.render(f)
+        assert np.array_equal(small, pool), f"{model} frame {k} flags={flags}: 128-entry pools"
+        with gpu.switch("rt_legacy"):
+            legacy = gpu.render(f)
+        assert np.array_equal(legacy, pool), f"{model} frame {k} flags={flags}: job pipeline"
         if k == 3 and size[0] <= 1280:
-            assert_parity(wave, pyport.render(s, f), f"{model} {size} frame {k} flags={flags}")
+            assert_parity(pool, pyport.render(s, f), f"{model} {size} frame {k} flags={flags}")
 
 
 @pytest.mark.parametrize("model", ["chessboard.tri", "dragon_vis.ply", "trainColor.tri"])
-def test_root_box_screen_rectangle_culls_nothing_visible(rb, load_scene, gpu, monkeypatch, model):
+def test_root_box_screen_rectangle_culls_nothing_visible(rb, load_scene, gpu, model):
     """K0 skips ray construction for pixels outside a conservative screen rectangle of the root box; the frame must be
     identical to the one where every pixel's ray takes the root test (several orbit positions, two aspect ratios)."""
     import numpy as np
@@ -171,9 +166,8 @@ def test_root_box_screen_rectangle_culls_nothing_visible(rb, load_scene, gpu, mo
         for (w, h) in ((640, 360), (320, 480)):
             f = rb.make_frame(rb.MODE_RAYTRACE, w, h, cam, flags=1 | 4)
             culled = gpu.render(f)
-            monkeypatch.setenv("B200R_NO_ROOT_RECT", "1")
-            full = gpu.render(f)
-            monkeypatch.delenv("B200R_NO_ROOT_RECT")
+            with gpu.switch("no_root_rect"):
+                full = gpu.render(f)
             assert np.array_equal(culled, full), f"{model} frame {k} {w}x{h}"
 
 
