@@ -20,6 +20,9 @@ struct Switches {
     int mlaa_nobatch = 0;         // MLAA walks load one word per step
     int no_frame_overlap = 0;     // b200r_render_async keeps ray-traced frames on one stream
     int bvh_serial_split = 0;     // BVH build: one thread per node in every level
+    int pool_policy = 0;          // rt_pool_kernel: how the inner pool is popped (rt_pool.cu PoolParams)
+    int pool_leaf_min = 0, pool_sort_min = 0, pool_shade_min = 0, pool_refill_min = 0, pool_low_water = 0, pool_dry = 0;   // rt_pool_kernel thresholds (0 = built-in)
+    int pool_no_scatter = 0;      // rt_pool_kernel: deal whole 8x4 tiles to warps (centre-out) instead of scattered 4-pixel groups
     int pool_stats = 0;           // rt_pool_kernel adds its per-phase iteration / lane counts to the work counters (tools/pool_stats.py)
 };
 
@@ -70,9 +73,9 @@ cudaError_t launch_bvh_build(const float* h_vertPos, int strideFloats, uint32_t 
 // rt_pool.cu: the pooled traversal kernel (clears the frame, then writes lit pixels / hit records)
 bool pool_supported(const DeviceScene& sc);
 cudaError_t rt_pool_configure();            // once per device: opt in to > 48 KB of dynamic shared memory
-cudaError_t launch_rt_pool(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, bool fused, bool prune, bool smallCap,
-                           bool noRootRect, unsigned* pixelCounter, void* hits, unsigned* hitCount, int numSMs, cudaStream_t stream,
-                           int& launches, DeviceCounters* stats = nullptr);
+cudaError_t launch_rt_pool(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, bool fused, bool prune, const Switches& sw,
+                           unsigned* pixelCounter, void* hits, unsigned* hitCount, int numSMs, cudaStream_t stream, int& launches,
+                           DeviceCounters* stats = nullptr);
 cudaError_t launch_division_selftest(unsigned long long samples, uint32_t seed, unsigned long long* d_mismatches,
                                      float* d_firstBad, int numSMs, cudaStream_t stream);
 cudaError_t launch_deinterleave(const uint32_t* gathered, uint32_t* frame, uint32_t W, uint32_t H, uint32_t P,

@@ -38,48 +38,40 @@ namespace {
 
 constexpr int POOL_WARPS = 8;            // warps per CTA (independent of each other)
 constexpr int POOL_CTAS_PER_SM = 3;
-constexpr int CAP_L = 128;               // leaf pool: < 32 waiting + at most 64 pushed per inner iteration (+ 32 roots)
+constexpr int CAP_L = 128;               // leaf pool: < LEAF_MIN waiting + at most 64 pushed per inner iteration (+ 32 roots)
+// scheduling thresholds (defaults; developer switches pool_* override them for tuning)
 constexpr int LEAF_MIN = 32;             // run a leaf iteration as soon as this many leaves wait
-constexpr int SHADE_MIN = 8;             // resolve finished slots once this many wait
+constexpr int SORT_MIN = 8;              // look at finished slots once this many wait (or the warp is running dry)
+constexpr int SHADE_MIN = 12;            // shade resolved hits once this many wait (or the warp is running dry)
 constexpr int REFILL_MIN = 8;            // take new pixels once this many slots are free ...
-constexpr int LOW_WATER = 48;            // ... and fewer than this many inner entries are pending
+constexpr int LOW_WATER = 32;            // ... and fewer than this many hot entries are pending
+constexpr int DRY = 16;                  // "running dry": fewer inner entries than this are pending
 constexpr uint32_t ITEM_LEAF = 0x80000000u;
 constexpr uint32_t ITEM_INDEX_MASK = 0x03FFFFFFu;     // 26 bits: inner record id or list position
+constexpr uint32_t ITEM_REF_MASK = ITEM_LEAF | ITEM_INDEX_MASK;
 constexpr int ITEM_SLOT_SHIFT = 26;
 constexpr unsigned long long KEY_EMPTY = ((unsigned long long)0x7F7FFFFFu << 32) | 0xFFFFFFFFull;   // (FLT_MAX, no list position)
 
+// Per-warp state in shared memory. The inner-node pool is ONE array with two stacks: HOT entries (the nearer child of the
+// node just processed - the depth-first continuation of its ray) grow up from index 0, COLD entries (the farther child, which
+// the reference's loop would visit after the whole near subtree) grow down from the end. Lanes pop hot entries first and fill
+// up with cold ones, newest first: with many rays in the warp every ray advances depth-first, nearest box first, and what it
+// finds prunes its cold entries before anyone fetches them; with few rays left the spare lanes walk the cold entries of the
+// same rays, which is what keeps a long ray from becoming the frame's critical path.
 template <int CAP_I>
 struct __align__(16) WarpPool {
-    uint2 ipool[CAP_I];                  // pending inner nodes of all slots
+    uint2 ipool[CAP_I];                  // {leaf flag | slot | index, entry distance of the node's box}
     uint2 lpool[CAP_L];                  // pending leaves
-    float4 ro[32];                       // slot: ray origin, pruning slack (+inf: never prune)
-    float4 rd[32];                       // slot: ray direction, w = 1 if the shared-reciprocal divide applies
-    float4 rr[32];                       // slot: refined reciprocals of the direction, w = bits(triangle to skip, or -1)
+    float4 ro[32];                       // slot: ray origin, pruning slack (+inf: never prune; -inf: ray finished, drop its entries)
+    float4 rd[32];                       // slot: ray direction
+    float4 rr[32];                       // slot: refined reciprocals of the direction, w = bits(triangle to skip): >= 0 marks a SHADOW ray
     unsigned long long key[32];          // slot: (bits(best hitZ) << 32) | list position; shadow slots: (bits(light distance^2) << 32)
     int pend[32];                        // slot: pool entries not yet processed
     uint32_t pix[32];                    // slot: (packed row << 16) | x
     uint32_t lit[32], shd[32];           // shadow slots: the two possible pixel words
-    uint32_t state[32];                  // bit 0: shadow ray, bit 1: occluded
 };
 
-__device__ __forceinline__ uint32_t make_item(uint32_t ref, uint32_t slot)
-{
-    return (ref & (ITEM_LEAF | ITEM_INDEX_MASK)) | (slot << ITEM_SLOT_SHIFT);
-}
-
-struct SlotRay { RayPrep rp; float slack; int avoid; };
-
-template <class POOL>
-__device__ __forceinline__ SlotRay load_slot_ray(const POOL& P, uint32_t slot, const float4& ro)
-{
-    const float4 rd = P.rd[slot], rr = P.rr[slot];
-    SlotRay s;
-    s.rp.o = mkv3(ro.x, ro.y, ro.z); s.rp.d = mkv3(rd.x, rd.y, rd.z); s.rp.r = mkv3(rr.x, rr.y, rr.z);
-    s.rp.fast = rd.w != 0.f;
-    s.slack = ro.w;
-    s.avoid = __float_as_int(rr.w);
-    return s;
-}
+__device__ __forceinline__ uint32_t make_item(uint32_t ref, uint32_t slot) { return (ref & ITEM_REF_MASK) | (slot << ITEM_SLOT_SHIFT); }
 
 __device__ __forceinline__ bool pruned(float tnear, float slack, float best)
 {
@@ -87,28 +79,44 @@ __device__ __forceinline__ bool pruned(float tnear, float slack, float best)
     return e > 0.f && (e * e) * 0.99999f > best;
 }
 
+// RayIntersectsBox (reference src/Raytracer.cc:99-151) for rays inside the shared-reciprocal domain (rt_common.cuh "Division"):
+// every quotient is finite there, so the compare-and-swap ladder of the reference collapses to min/max - the same values up to
+// the sign of a zero, which neither `Tnear > Tfar` nor `Tfar < 0` can see - and the per-axis early returns to the final test.
+__device__ __forceinline__ bool box_fast(const float4& o, const float4& d, const float4& r, float lox, float hix, float loy, float hiy,
+                                         float loz, float hiz, float& tnear)
+{
+    const float x1 = div_shared_rcp(lox - o.x, d.x, r.x), x2 = div_shared_rcp(hix - o.x, d.x, r.x);
+    const float y1 = div_shared_rcp(loy - o.y, d.y, r.y), y2 = div_shared_rcp(hiy - o.y, d.y, r.y);
+    const float z1 = div_shared_rcp(loz - o.z, d.z, r.z), z2 = div_shared_rcp(hiz - o.z, d.z, r.z);
+    const float tn = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fminf(z1, z2));
+    const float tf = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2));
+    tnear = tn;
+    return !(tn > tf) && !(tf < 0.f);
+}
+
 // The triangles of one leaf against one ray, in list order (reference src/Raytracer.cc:235-298). Closest-hit rays fold
 // improving hits into `bestK`; shadow rays return true at the first triangle that is nearer to the light than the origin is.
-__device__ __forceinline__ bool intersect_leaf(const DeviceScene& sc, const RayPrep& rp, uint32_t li, bool isShadow, int avoid,
+__device__ __forceinline__ bool intersect_leaf(const DeviceScene& sc, const V3& o, const V3& d, uint32_t li, int avoid,
                                                const V3& lightPos, float lightDistSq, unsigned long long& bestK)
 {
+    const bool isShadow = avoid >= 0;
     const float4* rec = sc.leaftris + 5 * (size_t)li;
     for (;; rec += 5, li++) {
         const float4 q4 = __ldg(rec + 4), q0 = __ldg(rec + 0), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
         const uint32_t tw = __float_as_uint(q4.w);
         const bool last = (tw & 0x40000000u) != 0;
         const V3 n = mkv3(q0.x, q0.y, q0.z);
-        bool alive = !(isShadow && (int)(tw & 0x3fffffffu) == avoid);      // avoidSelf
+        bool alive = (int)(tw & 0x3fffffffu) != avoid;                      // avoidSelf (avoid = -1 for primary rays)
         if (alive && !(tw & 0x80000000u)) {                                 // doCulling && !twoSided
-            const V3 fromTriToOrigin = rp.o - mkv3(q4.x, q4.y, q4.z);
+            const V3 fromTriToOrigin = o - mkv3(q4.x, q4.y, q4.z);
             if (dot3(fromTriToOrigin, n) < 0.f) alive = false;
         }
         if (alive) {
-            const float k = dot3(n, rp.d);
+            const float k = dot3(n, d);
             if (k != 0.f) {
-                const float s = (q0.w - dot3(n, rp.o)) / k;
+                const float s = (q0.w - dot3(n, o)) / k;
                 if (s > 0.f && s > 1e-5f) {                                 // behind the origin / NUDGE_FACTOR
-                    const V3 hit = rp.d * s + rp.o;
+                    const V3 hit = d * s + o;
                     const float kt1 = dot3(mkv3(q1.x, q1.y, q1.z), hit) - q1.w;
                     if (!(kt1 < 0.f)) {
                         const float kt2 = dot3(mkv3(q2.x, q2.y, q2.z), hit) - q2.w;
@@ -118,7 +126,7 @@ __device__ __forceinline__ bool intersect_leaf(const DeviceScene& sc, const RayP
                                 if (isShadow) {
                                     if (distancesq3(lightPos, hit) < lightDistSq) return true;
                                 } else {
-                                    const float hitZ = distancesq3(rp.o, hit);
+                                    const float hitZ = distancesq3(o, hit);
                                     if (hitZ < FLT_MAX) {                   // the reference starts from FLT_MAX with a strict `<`
                                         const unsigned long long k64 = ((unsigned long long)__float_as_uint(hitZ) << 32) | li;
                                         if (k64 < bestK) bestK = k64;
@@ -134,34 +142,79 @@ __device__ __forceinline__ bool intersect_leaf(const DeviceScene& sc, const RayP
     }
 }
 
-// Both children of inner record `id` against the ray: which survive, and the entry distances of their boxes.
-// A leaf child has no box test in the reference (src/Raytracer.cc:224-229): it survives unless empty, and carries `tHere`, the
-// entry distance of the node being processed (its triangles lie inside that box too).
-__device__ __forceinline__ void test_children(const DeviceScene& sc, const RayPrep& rp, uint32_t id, float tHere, float slack, float best,
-                                              uint32_t& L, uint32_t& R, bool& hitL, bool& hitR, float& tL, float& tR)
+// Cold path: one lane walks a whole subtree depth-first with a private stack - the reference's own loop with near-first order
+// and pruning. Used for rays outside the shared-reciprocal domain (a zero direction component: they take the reference's
+// `dir == 0` rule, ray_box<false>) and when a pool is about to overflow. Results go where the pooled lanes put theirs.
+__device__ __noinline__ void walk_subtree(const DeviceScene& sc, const RayPrep rp, const int avoid, const V3 lightPos, uint32_t cur, float tcur,
+                                          unsigned long long* key, const volatile float* slackWord)
 {
-    const float4* rec = sc.wnodes + 4 * (size_t)id;
-    const float4 bx = __ldg(rec + 0), by = __ldg(rec + 1), bz = __ldg(rec + 2), rf = __ldg(rec + 3);
-    L = __float_as_uint(rf.x); R = __float_as_uint(rf.y);
-    tL = tHere; tR = tHere;
-    if (L & REF_LEAF) hitL = (L != REF_EMPTY);
-    else hitL = rp.fast ? ray_box<true>(rp, bx.x, bx.y, by.x, by.y, bz.x, bz.y, &tL) : ray_box<false>(rp, bx.x, bx.y, by.x, by.y, bz.x, bz.y, &tL);
-    if (R & REF_LEAF) hitR = (R != REF_EMPTY);
-    else hitR = rp.fast ? ray_box<true>(rp, bx.z, bx.w, by.z, by.w, bz.z, bz.w, &tR) : ray_box<false>(rp, bx.z, bx.w, by.z, by.w, bz.z, bz.w, &tR);
-    const uint32_t unprunable = __float_as_uint(rf.z);        // bit0/bit1: L/R subtree holds a triangle that failed the upload check
-    if (unprunable & 1u) tL = -FLT_MAX;
-    if (unprunable & 2u) tR = -FLT_MAX;
-    if (hitL && pruned(tL, slack, best)) hitL = false;
-    if (hitR && pruned(tR, slack, best)) hitR = false;
+    uint32_t stk[B200R_BVH_STACK_SIZE]; float tst[B200R_BVH_STACK_SIZE];
+    int sp = 0;
+    for (;;) {
+        const unsigned long long k0 = *reinterpret_cast<volatile unsigned long long*>(key);
+        const float best = __uint_as_float((uint32_t)(k0 >> 32));
+        const float slack = *slackWord;
+        bool pop = true;
+        if (cur != REF_EMPTY && !pruned(tcur, slack, best)) {
+            if (cur & REF_LEAF) {
+                unsigned long long bestK = k0;
+                if (intersect_leaf(sc, rp.o, rp.d, cur & ITEM_INDEX_MASK, avoid, lightPos, best, bestK)) {
+                    *const_cast<float*>(slackWord) = -__int_as_float(0x7f800000);     // occluded: every other entry of the ray is dropped
+                    return;
+                }
+                if (bestK < k0) atomicMin(key, bestK);
+            } else {
+                const float4* rec = sc.wnodes + 4 * (size_t)cur;
+                const float4 bx = __ldg(rec + 0), by = __ldg(rec + 1), bz = __ldg(rec + 2), rf = __ldg(rec + 3);
+                const uint32_t L = __float_as_uint(rf.x), R = __float_as_uint(rf.y);
+                bool hitL, hitR; float tL = tcur, tR = tcur;
+                if (L & REF_LEAF) hitL = (L != REF_EMPTY);
+                else hitL = rp.fast ? ray_box<true>(rp, bx.x, bx.y, by.x, by.y, bz.x, bz.y, &tL) : ray_box<false>(rp, bx.x, bx.y, by.x, by.y, bz.x, bz.y, &tL);
+                if (R & REF_LEAF) hitR = (R != REF_EMPTY);
+                else hitR = rp.fast ? ray_box<true>(rp, bx.z, bx.w, by.z, by.w, bz.z, bz.w, &tR) : ray_box<false>(rp, bx.z, bx.w, by.z, by.w, bz.z, bz.w, &tR);
+                const uint32_t unprunable = __float_as_uint(rf.z);
+                if (unprunable & 1u) tL = -FLT_MAX;
+                if (unprunable & 2u) tR = -FLT_MAX;
+                if (hitL && pruned(tL, slack, best)) hitL = false;
+                if (hitR && pruned(tR, slack, best)) hitR = false;
+                if (hitL && hitR) {
+                    const bool rFirst = tR < tL;
+                    stk[sp] = rFirst ? L : R; tst[sp] = rFirst ? tL : tR; sp++;
+                    cur = rFirst ? R : L; tcur = rFirst ? tR : tL; pop = false;
+                } else if (hitL) { cur = L; tcur = tL; pop = false; }
+                else if (hitR) { cur = R; tcur = tR; pop = false; }
+            }
+        }
+        if (pop) {
+            if (sp == 0) return;
+            --sp; cur = stk[sp]; tcur = tst[sp];
+        }
+    }
 }
+
+// How pixels are dealt to warps and how the inner pool is popped (PoolParams.policy, developer switch pool_policy):
+//   0  hot entries first, spare lanes take cold ones (depth-first per ray while the warp has enough rays)
+//   1  one stack: the farther child is pushed under the nearer one and both are popped as they come (breadth grows fast)
+//   2  like 0, but up to 8 lanes always go to cold entries
+struct PoolParams {
+    int4 tiles;                     // first tile column / row, tile columns / rows of the screen rectangle that can contain the model
+    int prune, policy;
+    int leafMin, sortMin, shadeMin, refillMin, lowWater, dry;
+    unsigned scatterMul;            // 0: tiles are dealt in centre-out order, 32 neighbouring pixels per grab; else: 4-pixel groups
+    unsigned nGroups, groupsPerRow; //    are dealt in the order (q * scatterMul) mod nGroups, so every warp holds a cross-section
+    unsigned long long scatterInv;  //    of the frame instead of one tile (floor(2^64 / nGroups), for the modulo)
+};
 
 // STATS (developer switch pool_stats): per-phase iteration / lane counts are added to DeviceCounters (tools/pool_stats.py).
 template <bool FUSED, int CAP_I, bool STATS = false>
 __global__ void __launch_bounds__(POOL_WARPS * 32, POOL_CTAS_PER_SM)
-rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsigned* __restrict__ pixelCounter, int4 tiles,
-               HitRecord* __restrict__ hits, unsigned* __restrict__ hitCount, int prune, DeviceCounters* __restrict__ stats)
+rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsigned* __restrict__ pixelCounter, PoolParams pp,
+               HitRecord* __restrict__ hits, unsigned* __restrict__ hitCount, DeviceCounters* __restrict__ stats)
 {
-    unsigned st_it[5] = {0, 0, 0, 0, 0}, st_ln[5] = {0, 0, 0, 0, 0}, st_drop = 0, st_max = 0;   // inner, leaf, resolve, refill, guard
+    const int4 tiles = pp.tiles;
+    const int prune = pp.prune, policy = pp.policy;
+    const int LEAF_MIN = pp.leafMin, SORT_MIN = pp.sortMin, SHADE_MIN = pp.shadeMin, REFILL_MIN = pp.refillMin, LOW_WATER = pp.lowWater, DRY = pp.dry;
+    unsigned st_it[5] = {0, 0, 0, 0, 0}, st_ln[5] = {0, 0, 0, 0, 0}, st_drop = 0, st_cold = 0;   // inner, leaf, resolve, refill, guard
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Pool = WarpPool<CAP_I>;
     Pool& P = reinterpret_cast<Pool*>(smem_raw)[threadIdx.x >> 5];
@@ -175,13 +228,13 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
     const float INF = __int_as_float(0x7f800000);
 
     // warp-uniform bookkeeping
-    int icount = 0, lcount = 0;
-    unsigned freeMask = FULL, doneMask = 0u;
+    int hcount = 0, ccount = 0, lcount = 0;         // hot / cold inner entries, leaves
+    unsigned freeMask = FULL, doneMask = 0u, shadeMask = 0u;       // slots: free / finished, not looked at yet / resolved hits waiting to be shaded
     bool exhausted = (total == 0u);
 
     for (;;) {
         // ------------------------------------------------------------------ leaves, 32 at a time
-        if (lcount >= LEAF_MIN || (lcount > 0 && icount == 0)) {
+        if (lcount >= LEAF_MIN || (lcount > 0 && hcount + ccount == 0)) {
             const int n = min(32, lcount);
             lcount -= n;
             if (STATS) { st_it[1]++; st_ln[1] += n; }
@@ -190,14 +243,14 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
                 const uint2 it = P.lpool[lcount + n - 1 - (int)lane];
                 slot = (it.x >> ITEM_SLOT_SHIFT) & 31u;
                 const float4 ro = P.ro[slot];
-                const uint32_t st = P.state[slot];
                 const unsigned long long k0 = P.key[slot];
                 const float best = __uint_as_float((uint32_t)(k0 >> 32));
-                if (!(st & 2u) && !pruned(__uint_as_float(it.y), ro.w, best)) {
-                    const SlotRay s = load_slot_ray(P, slot, ro);
+                if (!pruned(__uint_as_float(it.y), ro.w, best)) {
+                    const float4 rd = P.rd[slot];
                     unsigned long long bestK = k0;
-                    const bool occ = intersect_leaf(sc, s.rp, it.x & ITEM_INDEX_MASK, (st & 1u) != 0u, s.avoid, lightPos, best, bestK);
-                    if (occ) P.state[slot] = 3u;
+                    const bool occ = intersect_leaf(sc, mkv3(ro.x, ro.y, ro.z), mkv3(rd.x, rd.y, rd.z), it.x & ITEM_INDEX_MASK,
+                                                    __float_as_int(P.rr[slot].w), lightPos, best, bestK);
+                    if (occ) P.ro[slot].w = -INF;
                     else if (bestK < k0) atomicMin(&P.key[slot], bestK);
                 }
                 fin = atomicSub(&P.pend[slot], 1) == 1;
@@ -206,55 +259,75 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
             __syncwarp();
             continue;
         }
-        // ------------------------------------------------------------------ finished slots: black / shade + shadow ray / hit record
+        // ------------------------------------------------------------------ finished slots: shadow rays write their pixel, primary rays
+        // that pierced nothing are done (the frame was cleared to black), resolved hits queue up for shading
+        // (every branch that pushes checks the room left in the inner pool: an inner iteration needs 64 free entries - each of
+        // its <= 32 lanes may push two - or it runs as the overflow guard; shading / refilling push at most 32)
+        const int room = CAP_I - (hcount + ccount);
+        const bool dry = hcount + ccount < DRY;
         const int ndone = __popc(doneMask);
-        if (ndone >= SHADE_MIN || (ndone > 0 && icount == 0)) {
-            if (STATS) { st_it[2]++; st_ln[2] += ndone; }
-            bool freed = false, arm = false; uint32_t slot = 0;
-            bool record = false; int tri = -1; V3 hitp = eye; float kAB = 0.f, kBC = 0.f, kCA = 0.f;
+        if (ndone >= SORT_MIN || (ndone > 0 && dry)) {
+            bool freed = false, hit = false; uint32_t slot = 0;
             if ((int)lane < ndone) {
                 slot = __fns(doneMask, 0u, (int)lane + 1);
-                const uint32_t st = P.state[slot];
+                if (__float_as_int(P.rr[slot].w) >= 0) {
+                    const uint32_t pix = P.pix[slot];
+                    out[(size_t)(pix >> 16) * fp.W + (pix & 0xffffu)] = (P.ro[slot].w == -INF) ? P.shd[slot] : P.lit[slot];
+                    freed = true;
+                } else if (P.key[slot] == KEY_EMPTY) freed = true;
+                else hit = true;
+            }
+            freeMask |= __reduce_or_sync(FULL, freed ? (1u << slot) : 0u);
+            shadeMask |= __reduce_or_sync(FULL, hit ? (1u << slot) : 0u);
+            doneMask = 0u;
+            continue;
+        }
+        // ------------------------------------------------------------------ resolved hits: shade + shadow ray / hit record
+        const int nshade = __popc(shadeMask);
+        if ((nshade >= SHADE_MIN || (nshade > 0 && dry)) && room >= 32) {
+            if (STATS) { st_it[2]++; st_ln[2] += nshade; }
+            bool freed = false, arm = false; uint32_t slot = 0;
+            bool record = false; int tri = -1; V3 hitp = eye; float kAB = 0.f, kBC = 0.f, kCA = 0.f;
+            if ((int)lane < nshade) {
+                slot = __fns(shadeMask, 0u, (int)lane + 1);
                 const uint32_t pix = P.pix[slot];
                 const size_t o = (size_t)(pix >> 16) * fp.W + (pix & 0xffffu);
                 freed = true;
-                if (st & 1u) out[o] = (st & 2u) ? P.shd[slot] : P.lit[slot];
-                else {
-                    const unsigned long long k = P.key[slot];
-                    if (k != KEY_EMPTY) {          // else: pierced nothing - the frame was cleared to black
-                        const float4 rd = P.rd[slot];
-                        reconstruct_hit(sc, eye, mkv3(rd.x, rd.y, rd.z), (uint32_t)k, tri, hitp, kAB, kBC, kCA);
-                        if (FUSED) {
-                            uint32_t pixLit, pixShadow; V3 sdir; float ldsq;
-                            shade_one_light(sc, fp, eye, tri, hitp, kAB, kBC, kCA, pixLit, pixShadow, sdir, ldsq);
-                            if (!(fp.flags & B200R_F_SHADOWS) || pixLit == pixShadow) out[o] = pixLit;   // the shadow ray cannot change this pixel
-                            else {
-                                const RayPrep rp = prep_ray(sc, hitp, sdir);
-                                bool enter = true;
-                                if (!(sc.root_ref & REF_LEAF))
-                                    enter = rp.fast ? ray_box<true>(rp, sc.root_lo[0], sc.root_hi[0], sc.root_lo[1], sc.root_hi[1], sc.root_lo[2], sc.root_hi[2])
-                                                    : ray_box<false>(rp, sc.root_lo[0], sc.root_hi[0], sc.root_lo[1], sc.root_hi[1], sc.root_lo[2], sc.root_hi[2]);
-                                else if (sc.root_ref == REF_EMPTY) enter = false;
-                                if (!enter) out[o] = pixLit;
-                                else {
-                                    P.ro[slot] = make_float4(hitp.x, hitp.y, hitp.z, INF);         // any-hit ray: no distance pruning
-                                    P.rd[slot] = make_float4(sdir.x, sdir.y, sdir.z, rp.fast ? 1.f : 0.f);
-                                    P.rr[slot] = make_float4(rp.r.x, rp.r.y, rp.r.z, __int_as_float(tri));
-                                    P.key[slot] = (unsigned long long)__float_as_uint(ldsq) << 32;
-                                    P.pend[slot] = 1; P.lit[slot] = pixLit; P.shd[slot] = pixShadow; P.state[slot] = 1u;
-                                    freed = false; arm = true;
-                                }
+                const unsigned long long k = P.key[slot];
+                const float4 rd = P.rd[slot];
+                reconstruct_hit(sc, eye, mkv3(rd.x, rd.y, rd.z), (uint32_t)k, tri, hitp, kAB, kBC, kCA);
+                if (FUSED) {
+                    uint32_t pixLit, pixShadow; V3 sdir; float ldsq;
+                    shade_one_light(sc, fp, eye, tri, hitp, kAB, kBC, kCA, pixLit, pixShadow, sdir, ldsq);
+                    if (!(fp.flags & B200R_F_SHADOWS) || pixLit == pixShadow) out[o] = pixLit;   // the shadow ray cannot change this pixel
+                    else {
+                        const RayPrep rp = prep_ray(sc, hitp, sdir);
+                        bool enter = true;
+                        if (!(sc.root_ref & REF_LEAF))
+                            enter = rp.fast ? ray_box<true>(rp, sc.root_lo[0], sc.root_hi[0], sc.root_lo[1], sc.root_hi[1], sc.root_lo[2], sc.root_hi[2])
+                                            : ray_box<false>(rp, sc.root_lo[0], sc.root_hi[0], sc.root_lo[1], sc.root_hi[1], sc.root_lo[2], sc.root_hi[2]);
+                        else if (sc.root_ref == REF_EMPTY) enter = false;
+                        if (!enter) out[o] = pixLit;
+                        else {
+                            P.ro[slot] = make_float4(hitp.x, hitp.y, hitp.z, INF);         // any-hit ray: no distance pruning
+                            P.rd[slot] = make_float4(sdir.x, sdir.y, sdir.z, 0.f);
+                            P.rr[slot] = make_float4(rp.r.x, rp.r.y, rp.r.z, __int_as_float(tri));
+                            P.key[slot] = (unsigned long long)__float_as_uint(ldsq) << 32;
+                            if (rp.fast) { P.pend[slot] = 1; P.lit[slot] = pixLit; P.shd[slot] = pixShadow; freed = false; arm = true; }
+                            else {          // outside the shared-reciprocal domain: walked here, by this lane
+                                walk_subtree(sc, rp, tri, lightPos, sc.root_ref, -FLT_MAX, &P.key[slot], &P.ro[slot].w);
+                                out[o] = (P.ro[slot].w == -INF) ? pixShadow : pixLit;
                             }
-                        } else record = true;
+                        }
                     }
-                }
+                } else record = true;
             }
             if (FUSED) {
                 const unsigned am = __ballot_sync(FULL, arm);
                 if (am) {
                     const uint2 item = make_uint2(make_item(sc.root_ref, slot), __float_as_uint(-FLT_MAX));
                     if (sc.root_ref & REF_LEAF) { if (arm) P.lpool[lcount + __popc(am & lt)] = item; lcount += __popc(am); }
-                    else { if (arm) P.ipool[icount + __popc(am & lt)] = item; icount += __popc(am); }
+                    else { if (arm) P.ipool[hcount + __popc(am & lt)] = item; hcount += __popc(am); }
                 }
             } else {
                 const unsigned hm = __ballot_sync(FULL, record);
@@ -270,12 +343,12 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
                 }
             }
             freeMask |= __reduce_or_sync(FULL, freed ? (1u << slot) : 0u);
-            doneMask = 0u;
+            shadeMask = 0u;
             __syncwarp();
             continue;
         }
         // ------------------------------------------------------------------ new pixels into free slots
-        if (!exhausted && icount < LOW_WATER && (__popc(freeMask) >= REFILL_MIN || icount == 0)) {
+        if (!exhausted && hcount < LOW_WATER && room >= 32 && (__popc(freeMask) >= REFILL_MIN || hcount + ccount == 0)) {
             const int nfree = __popc(freeMask);
             unsigned base = 0;
             if (lane == 0) base = atomicAdd(pixelCounter, (unsigned)nfree);
@@ -284,11 +357,20 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
             const unsigned g = base + lane;
             bool enter = false; RayPrep rp; int x = 0, r = 0;
             if ((int)lane < nfree && g < total) {
-                const unsigned tile = g >> 5, l = g & 31u;
-                const int qrow = (int)(tile / (unsigned)ntx), off = (qrow + 1) >> 1;
-                const int trow = (qrow & 1) ? (nty >> 1) - off : (nty >> 1) + off;        // centre-out: the expensive tiles first
-                x = (tx0 + (int)(tile % (unsigned)ntx)) * 8 + (int)(l & 7u);
-                r = (ty0 + trow) * 4 + (int)(l >> 3);
+                if (pp.scatterMul) {
+                    const unsigned long long prod = (unsigned long long)(g >> 2) * pp.scatterMul;
+                    unsigned long long rem = prod - __umul64hi(prod, pp.scatterInv) * pp.nGroups;
+                    if (rem >= pp.nGroups) rem -= pp.nGroups;
+                    const unsigned q = (unsigned)rem;
+                    x = tx0 * 8 + (int)(q % pp.groupsPerRow) * 4 + (int)(g & 3u);
+                    r = ty0 * 4 + (int)(q / pp.groupsPerRow);
+                } else {
+                    const unsigned tile = g >> 5, l = g & 31u;
+                    const int qrow = (int)(tile / (unsigned)ntx), off = (qrow + 1) >> 1;
+                    const int trow = (qrow & 1) ? (nty >> 1) - off : (nty >> 1) + off;        // centre-out: the expensive tiles first
+                    x = (tx0 + (int)(tile % (unsigned)ntx)) * 8 + (int)(l & 7u);
+                    r = (ty0 + trow) * 4 + (int)(l >> 3);
+                }
                 if (x < (int)fp.W && r < (int)fp.n_rows) {
                     const int y = (int)fp.row_first + r * (int)fp.row_step;
                     rp = prep_ray(sc, eye, primary_ray(fp, x, y));
@@ -299,7 +381,7 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
             }
             const unsigned em = __ballot_sync(FULL, enter);
             if (STATS) { st_it[3]++; st_ln[3] += __popc(em); }
-            uint32_t slot = 0;
+            uint32_t slot = 0; bool walked = false;
             if (enter) {
                 slot = __fns(freeMask, 0u, __popc(em & lt) + 1);
                 float slack = INF;
@@ -309,105 +391,102 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
                     slack = 1e-4f * m + 1e-4f;
                 }
                 P.ro[slot] = make_float4(rp.o.x, rp.o.y, rp.o.z, slack);
-                P.rd[slot] = make_float4(rp.d.x, rp.d.y, rp.d.z, rp.fast ? 1.f : 0.f);
+                P.rd[slot] = make_float4(rp.d.x, rp.d.y, rp.d.z, 0.f);
                 P.rr[slot] = make_float4(rp.r.x, rp.r.y, rp.r.z, __int_as_float(-1));
                 P.key[slot] = KEY_EMPTY;
-                P.pend[slot] = 1; P.pix[slot] = ((uint32_t)r << 16) | (uint32_t)x; P.state[slot] = 0u;
-                const uint2 item = make_uint2(make_item(sc.root_ref, slot), __float_as_uint(-FLT_MAX));
-                if (sc.root_ref & REF_LEAF) P.lpool[lcount + __popc(em & lt)] = item;
-                else P.ipool[icount + __popc(em & lt)] = item;
+                P.pix[slot] = ((uint32_t)r << 16) | (uint32_t)x;
+                if (rp.fast) P.pend[slot] = 1;
+                else {              // outside the shared-reciprocal domain: walked here, by this lane, then resolved like any other
+                    walk_subtree(sc, rp, -1, lightPos, sc.root_ref, -FLT_MAX, &P.key[slot], &P.ro[slot].w);
+                    walked = true;
+                }
             }
-            if (sc.root_ref & REF_LEAF) lcount += __popc(em); else icount += __popc(em);
+            const unsigned pm = __ballot_sync(FULL, enter && !walked);
+            if (enter && !walked) {
+                const uint2 item = make_uint2(make_item(sc.root_ref, slot), __float_as_uint(-FLT_MAX));
+                if (sc.root_ref & REF_LEAF) P.lpool[lcount + __popc(pm & lt)] = item;
+                else P.ipool[hcount + __popc(pm & lt)] = item;
+            }
+            if (sc.root_ref & REF_LEAF) lcount += __popc(pm); else hcount += __popc(pm);
             freeMask &= ~__reduce_or_sync(FULL, enter ? (1u << slot) : 0u);
+            doneMask |= __reduce_or_sync(FULL, walked ? (1u << slot) : 0u);
             __syncwarp();
             continue;
         }
-        if (icount == 0) break;            // nothing pending, nothing waiting, no pixels left
+        if (hcount + ccount == 0) break;            // nothing pending, nothing waiting, no pixels left
 
-        // ------------------------------------------------------------------ inner nodes, 32 at a time
-        const int n = min(32, icount);
-        icount -= n;
-        bool fin = false; uint32_t slot = 0;
-        if (icount + n > CAP_I - 64) {
-            // (overflow guard) the pool is nearly full: each lane walks its entry's whole subtree depth-first with a private stack
-            if (STATS) { st_it[4]++; st_ln[4] += n; }
-            if ((int)lane < n) {
-                const uint2 it = P.ipool[icount + n - 1 - (int)lane];
-                slot = (it.x >> ITEM_SLOT_SHIFT) & 31u;
-                const float4 ro = P.ro[slot];
-                const SlotRay s = load_slot_ray(P, slot, ro);
-                const bool isShadow = (P.state[slot] & 1u) != 0u;
-                uint32_t stk[B200R_BVH_STACK_SIZE]; float tst[B200R_BVH_STACK_SIZE];
-                int sp = 0;
-                uint32_t cur = it.x & (ITEM_LEAF | ITEM_INDEX_MASK); float tcur = __uint_as_float(it.y);
-                for (;;) {
-                    const unsigned long long k0 = P.key[slot];
-                    const float best = __uint_as_float((uint32_t)(k0 >> 32));
-                    bool pop = true;
-                    if (!(P.state[slot] & 2u) && !pruned(tcur, s.slack, best)) {
-                        if (cur & ITEM_LEAF) {
-                            unsigned long long bestK = k0;
-                            if (intersect_leaf(sc, s.rp, cur & ITEM_INDEX_MASK, isShadow, s.avoid, lightPos, best, bestK)) P.state[slot] = 3u;
-                            else if (bestK < k0) atomicMin(&P.key[slot], bestK);
-                        } else {
-                            uint32_t L, R; bool hitL, hitR; float tL, tR;
-                            test_children(sc, s.rp, cur, tcur, s.slack, best, L, R, hitL, hitR, tL, tR);
-                            if (hitL && hitR) {
-                                const bool rFirst = tR < tL;
-                                stk[sp] = (rFirst ? L : R) & (ITEM_LEAF | ITEM_INDEX_MASK); tst[sp] = rFirst ? tL : tR; sp++;
-                                cur = (rFirst ? R : L) & (ITEM_LEAF | ITEM_INDEX_MASK); tcur = rFirst ? tR : tL; pop = false;
-                            } else if (hitL) { cur = L & (ITEM_LEAF | ITEM_INDEX_MASK); tcur = tL; pop = false; }
-                            else if (hitR) { cur = R & (ITEM_LEAF | ITEM_INDEX_MASK); tcur = tR; pop = false; }
-                        }
-                    }
-                    if (pop) {
-                        if (sp == 0) break;
-                        --sp; cur = stk[sp]; tcur = tst[sp];
-                    }
-                }
+        // ------------------------------------------------------------------ inner nodes, 32 at a time: hot entries first, then cold
+        int nh = min(32, hcount), nc = min(32 - nh, ccount);
+        if (policy == 2 && nc < 8 && ccount > nc) { nc = min(8, ccount); nh = min(nh, 32 - nc); }
+        const bool guard = room < 64;
+        uint2 it = make_uint2(0u, 0u);
+        const bool have = (int)lane < nh + nc;
+        if ((int)lane < nh) it = P.ipool[hcount - 1 - (int)lane];
+        else if (have) it = P.ipool[CAP_I - ccount + ((int)lane - nh)];
+        hcount -= nh; ccount -= nc;
+        bool fin = false;
+        const uint32_t slot = (it.x >> ITEM_SLOT_SHIFT) & 31u;
+        if (guard) {
+            // (overflow guard) the pool is nearly full: each lane walks its entry's whole subtree itself instead of expanding it
+            if (STATS) { st_it[4]++; st_ln[4] += nh + nc; }
+            if (have) {
+                const float4 ro = P.ro[slot], rd = P.rd[slot], rr = P.rr[slot];
+                RayPrep rp; rp.o = mkv3(ro.x, ro.y, ro.z); rp.d = mkv3(rd.x, rd.y, rd.z); rp.r = mkv3(rr.x, rr.y, rr.z); rp.fast = true;
+                walk_subtree(sc, rp, __float_as_int(rr.w), lightPos, it.x & ITEM_REF_MASK, __uint_as_float(it.y), &P.key[slot], &P.ro[slot].w);
                 fin = atomicSub(&P.pend[slot], 1) == 1;
             }
             doneMask |= __reduce_or_sync(FULL, fin ? (1u << slot) : 0u);
             __syncwarp();
             continue;
         }
-        if (STATS) { st_it[0]++; st_ln[0] += n; st_max = max(st_max, (unsigned)(icount + n)); }
-        uint32_t c0 = 0, c1 = 0; float t0 = 0.f, t1 = 0.f;          // children to push: c0 (far) first, c1 (near) on top of it
-        bool p0 = false, p1 = false;
-        if ((int)lane < n) {
-            const uint2 it = P.ipool[icount + n - 1 - (int)lane];
-            slot = (it.x >> ITEM_SLOT_SHIFT) & 31u;
+        if (STATS) { st_it[0]++; st_ln[0] += nh + nc; st_cold += nc; }
+        uint32_t cN = 0, cF = 0; float tN = 0.f, tF = 0.f;          // surviving children: the nearer one, the farther one
+        bool pN = false, pF = false;
+        if (have) {
             const float4 ro = P.ro[slot];
-            const uint32_t st = P.state[slot];
-            const float best = __uint_as_float((uint32_t)(P.key[slot] >> 32));
+            const float best = __uint_as_float(reinterpret_cast<const uint32_t*>(&P.key[slot])[1]);
             const float tHere = __uint_as_float(it.y);
             int delta = -1;
-            if (!(st & 2u) && !pruned(tHere, ro.w, best)) {
-                const SlotRay s = load_slot_ray(P, slot, ro);
-                uint32_t L, R; bool hitL, hitR; float tL, tR;
-                test_children(sc, s.rp, it.x & ITEM_INDEX_MASK, tHere, s.slack, best, L, R, hitL, hitR, tL, tR);
-                if (hitL && hitR) {
-                    const bool rFirst = tR < tL;                     // nearer child on top
-                    c0 = rFirst ? L : R; t0 = rFirst ? tL : tR; p0 = true;
-                    c1 = rFirst ? R : L; t1 = rFirst ? tR : tL; p1 = true;
-                    delta = 1;
-                } else if (hitL) { c1 = L; t1 = tL; p1 = true; delta = 0; }
-                else if (hitR) { c1 = R; t1 = tR; p1 = true; delta = 0; }
+            if (!pruned(tHere, ro.w, best)) {
+                const float4 rd = P.rd[slot], rr = P.rr[slot];
+                const float4* rec = sc.wnodes + 4 * (size_t)(it.x & ITEM_INDEX_MASK);
+                const float4 bx = __ldg(rec + 0), by = __ldg(rec + 1), bz = __ldg(rec + 2), rf = __ldg(rec + 3);
+                const uint32_t L = __float_as_uint(rf.x), R = __float_as_uint(rf.y);
+                // both boxes, unconditionally (straight-line code). A LEAF child has no box test in the reference
+                // (src/Raytracer.cc:224-229): it survives unless empty; its box only supplies a tighter entry distance.
+                float tL, tR;
+                bool hitL = box_fast(ro, rd, rr, bx.x, bx.y, by.x, by.y, bz.x, bz.y, tL);
+                bool hitR = box_fast(ro, rd, rr, bx.z, bx.w, by.z, by.w, bz.z, bz.w, tR);
+                if (L & REF_LEAF) { if (!hitL) tL = tHere; hitL = (L != REF_EMPTY); }
+                if (R & REF_LEAF) { if (!hitR) tR = tHere; hitR = (R != REF_EMPTY); }
+                const uint32_t unprunable = __float_as_uint(rf.z);        // bit0/bit1: L/R subtree holds a triangle that failed the upload check
+                if (unprunable & 1u) tL = -FLT_MAX;
+                if (unprunable & 2u) tR = -FLT_MAX;
+                if (hitL && pruned(tL, ro.w, best)) hitL = false;
+                if (hitR && pruned(tR, ro.w, best)) hitR = false;
+                const bool rFirst = hitR && (!hitL || tR < tL);
+                cN = rFirst ? R : L; tN = rFirst ? tR : tL; pN = hitL || hitR;
+                cF = rFirst ? L : R; tF = rFirst ? tL : tR; pF = hitL && hitR;
+                delta += (pN ? 1 : 0) + (pF ? 1 : 0);
             } else if (STATS) st_drop++;
             if (delta != 0) fin = (atomicAdd(&P.pend[slot], delta) + delta) == 0;
         }
         {
-            const bool i0 = p0 && !(c0 & REF_LEAF), i1 = p1 && !(c1 & REF_LEAF);
-            const bool l0 = p0 && (c0 & REF_LEAF), l1 = p1 && (c1 & REF_LEAF);
-            const unsigned bI0 = __ballot_sync(FULL, i0), bI1 = __ballot_sync(FULL, i1);
-            const unsigned bL0 = __ballot_sync(FULL, l0), bL1 = __ballot_sync(FULL, l1);
-            int io = icount + __popc(bI0 & lt) + __popc(bI1 & lt);
-            int lo = lcount + __popc(bL0 & lt) + __popc(bL1 & lt);
-            if (i0) P.ipool[io++] = make_uint2(make_item(c0, slot), __float_as_uint(t0));
-            if (l0) P.lpool[lo++] = make_uint2(make_item(c0, slot), __float_as_uint(t0));
-            if (i1) P.ipool[io] = make_uint2(make_item(c1, slot), __float_as_uint(t1));
-            if (l1) P.lpool[lo] = make_uint2(make_item(c1, slot), __float_as_uint(t1));
-            icount += __popc(bI0) + __popc(bI1);
+            const bool oneStack = policy == 1;
+            const bool hN = pN && !(cN & REF_LEAF), hF = pF && !(cF & REF_LEAF);      // inner children: near -> hot, far -> cold
+            const bool lN = pN && (cN & REF_LEAF), lF = pF && (cF & REF_LEAF);        // leaves: straight to the leaf pool
+            const unsigned bH = __ballot_sync(FULL, hN), bC = __ballot_sync(FULL, hF);
+            const unsigned bL0 = __ballot_sync(FULL, lF), bL1 = __ballot_sync(FULL, lN);
+            if (oneStack) {             // far children first, the near ones on top of them
+                if (hF) P.ipool[hcount + __popc(bC & lt)] = make_uint2(make_item(cF, slot), __float_as_uint(tF));
+                if (hN) P.ipool[hcount + __popc(bC) + __popc(bH & lt)] = make_uint2(make_item(cN, slot), __float_as_uint(tN));
+            } else {
+                if (hN) P.ipool[hcount + __popc(bH & lt)] = make_uint2(make_item(cN, slot), __float_as_uint(tN));
+                if (hF) P.ipool[CAP_I - 1 - ccount - __popc(bC & lt)] = make_uint2(make_item(cF, slot), __float_as_uint(tF));
+            }
+            if (lF) P.lpool[lcount + __popc(bL0 & lt)] = make_uint2(make_item(cF, slot), __float_as_uint(tF));
+            if (lN) P.lpool[lcount + __popc(bL0) + __popc(bL1 & lt)] = make_uint2(make_item(cN, slot), __float_as_uint(tN));
+            hcount += __popc(bH) + (oneStack ? __popc(bC) : 0); ccount += oneStack ? 0 : __popc(bC);
             lcount += __popc(bL0) + __popc(bL1);
         }
         doneMask |= __reduce_or_sync(FULL, fin ? (1u << slot) : 0u);
@@ -418,8 +497,9 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
         if (lane == 0) {
             for (int i = 0; i < 5; i++) { atomicAdd(&stats->v[2 * i], (unsigned long long)st_it[i]); atomicAdd(&stats->v[2 * i + 1], (unsigned long long)st_ln[i]); }
             atomicAdd(&stats->v[10], (unsigned long long)st_drop);
+            atomicAdd(&stats->v[8], (unsigned long long)st_cold << 32);      // packed beside the guard iterations
+            atomicMax(&stats->v[9], (unsigned long long)(st_it[0] + st_it[1] + st_it[2] + st_it[3] + st_it[4]));   // most iterations of any warp
         }
-        (void)st_max;
     }
 }
 
@@ -457,24 +537,43 @@ cudaError_t rt_pool_configure()
     return e;
 }
 
-cudaError_t launch_rt_pool(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, bool fused, bool prune, bool smallCap,
-                           bool noRootRect, unsigned* pixelCounter, void* hits, unsigned* hitCount, int numSMs, cudaStream_t stream,
-                           int& launches, DeviceCounters* stats)
+cudaError_t launch_rt_pool(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, bool fused, bool prune, const Switches& sw,
+                           unsigned* pixelCounter, void* hits, unsigned* hitCount, int numSMs, cudaStream_t stream, int& launches,
+                           DeviceCounters* stats)
 {
     cudaError_t e = cudaMemsetAsync(d_out, 0, (size_t)fp.W * fp.n_rows * 4, stream);        // black; the kernel writes lit pixels only
     if (e != cudaSuccess) return e;
-    const int4 bounds = noRootRect ? make_int4(0, 0, (int)fp.W - 1, (int)fp.H - 1) : root_screen_bounds(sc, fp);
-    const int4 tiles = tile_rect(fp, bounds);
-    if (tiles.z <= 0 || tiles.w <= 0) return cudaSuccess;
-    using K = void (*)(DeviceScene, FrameParams, uint32_t*, unsigned*, int4, HitRecord*, unsigned*, int, DeviceCounters*);
+    const int4 bounds = sw.no_root_rect ? make_int4(0, 0, (int)fp.W - 1, (int)fp.H - 1) : root_screen_bounds(sc, fp);
+    PoolParams pp;
+    pp.tiles = tile_rect(fp, bounds);
+    if (pp.tiles.z <= 0 || pp.tiles.w <= 0) return cudaSuccess;
+    pp.prune = prune ? 1 : 0;
+    pp.policy = sw.pool_policy;
+    pp.leafMin = sw.pool_leaf_min > 0 ? sw.pool_leaf_min : LEAF_MIN; pp.sortMin = sw.pool_sort_min > 0 ? sw.pool_sort_min : SORT_MIN;
+    pp.shadeMin = sw.pool_shade_min > 0 ? sw.pool_shade_min : SHADE_MIN; pp.refillMin = sw.pool_refill_min > 0 ? sw.pool_refill_min : REFILL_MIN;
+    pp.lowWater = sw.pool_low_water > 0 ? sw.pool_low_water : LOW_WATER; pp.dry = sw.pool_dry > 0 ? sw.pool_dry : DRY;
+    if (pp.leafMin > 32) pp.leafMin = 32;             // the leaf pool holds < leafMin + 64 + 32 entries
+    if (pp.lowWater > 64) pp.lowWater = 64;
+    pp.nGroups = (unsigned)pp.tiles.z * 2u * (unsigned)pp.tiles.w * 4u;
+    pp.groupsPerRow = (unsigned)pp.tiles.z * 2u;
+    pp.scatterMul = 0; pp.scatterInv = 0;
+    if (!sw.pool_no_scatter && pp.nGroups > 64) {
+        // a multiplier near nGroups / golden ratio, coprime to nGroups: consecutive groups land far apart
+        unsigned m = (unsigned)((double)pp.nGroups * 0.6180339887498949) | 1u;
+        auto gcd = [](unsigned a, unsigned b) { while (b) { const unsigned t = a % b; a = b; b = t; } return a; };
+        while (gcd(m, pp.nGroups) != 1u) m += 2;
+        pp.scatterMul = m % pp.nGroups;
+        pp.scatterInv = ~0ull / pp.nGroups;
+    }
+    using K = void (*)(DeviceScene, FrameParams, uint32_t*, unsigned*, PoolParams, HitRecord*, unsigned*, DeviceCounters*);
     K k; size_t smem;
-    if (smallCap) { k = fused ? rt_pool_kernel<true, 128> : rt_pool_kernel<false, 128>; smem = sizeof(WarpPool<128>) * POOL_WARPS; }
+    if (sw.pool_small) { k = fused ? rt_pool_kernel<true, 128> : rt_pool_kernel<false, 128>; smem = sizeof(WarpPool<128>) * POOL_WARPS; }
     else { k = fused ? rt_pool_kernel<true, 512> : rt_pool_kernel<false, 512>; smem = sizeof(WarpPool<512>) * POOL_WARPS; }
-    if (stats && !smallCap) k = fused ? rt_pool_kernel<true, 512, true> : rt_pool_kernel<false, 512, true>;
+    if (stats && !sw.pool_small) k = fused ? rt_pool_kernel<true, 512, true> : rt_pool_kernel<false, 512, true>;
     int grid = numSMs * POOL_CTAS_PER_SM;
-    const int needed = (tiles.z * tiles.w + POOL_WARPS - 1) / POOL_WARPS;       // one tile per warp is the least a warp can take
+    const int needed = (pp.tiles.z * pp.tiles.w + POOL_WARPS - 1) / POOL_WARPS;       // one tile per warp is the least a warp can take
     if (grid > needed) grid = needed;
-    k<<<grid, POOL_WARPS * 32, smem, stream>>>(sc, fp, d_out, pixelCounter, tiles, reinterpret_cast<HitRecord*>(hits), hitCount, prune ? 1 : 0, stats);
+    k<<<grid, POOL_WARPS * 32, smem, stream>>>(sc, fp, d_out, pixelCounter, pp, reinterpret_cast<HitRecord*>(hits), hitCount, stats);
     launches += 1;
     return cudaGetLastError();
 }

@@ -154,6 +154,27 @@ def test_pool_overflow_guard_and_legacy_pipeline_agree(rb, pyport, load_scene, g
             assert_parity(pool, pyport.render(s, f), f"{model} {size} frame {k} flags={flags}")
 
 
+@pytest.mark.parametrize("model,size", [("chessboard.tri", (1920, 1080)), ("dragon_vis.ply", (801, 603)), ("torus.ply", (64, 48))])
+def test_pool_scheduling_variants_change_nothing(rb, load_scene, gpu, model, size):
+    """How rt_pool_kernel deals pixels to warps (scattered 4-pixel groups / whole tiles) and pops its pool (policies 0, 1, 2) is
+    scheduling only: every combination must give the same frame, fused and generic configurations."""
+    import numpy as np
+    s = load_scene(model)
+    gpu.upload(s)
+    cam = rb.Orbit.cameras([21])[21]
+    for flags in (1 | 4, 1 | 2 | 4):
+        f = rb.make_frame(rb.MODE_RAYTRACE, size[0], size[1], cam, flags=flags)
+        base = gpu.render(f)
+        for scatter_off in (0, 1):
+            for policy in (0, 1, 2):
+                gpu.set_switch("pool_no_scatter", scatter_off); gpu.set_switch("pool_policy", policy)
+                try:
+                    got = gpu.render(f)
+                finally:
+                    gpu.set_switch("pool_no_scatter", 0); gpu.set_switch("pool_policy", 0)
+                assert np.array_equal(got, base), f"{model} flags={flags} no_scatter={scatter_off} policy={policy}"
+
+
 @pytest.mark.parametrize("model", ["chessboard.tri", "dragon_vis.ply", "trainColor.tri"])
 def test_root_box_screen_rectangle_culls_nothing_visible(rb, load_scene, gpu, model):
     """K0 skips ray construction for pixels outside a conservative screen rectangle of the root box; the frame must be

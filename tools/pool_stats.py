@@ -19,6 +19,6 @@ g.render(f)
 c = list(g.counters().values())
 names = ["inner", "leaf", "resolve", "refill", "guard"]
 out = {n: {"iterations": c[2 * i], "lanes": c[2 * i + 1], "lanes_per_iteration": round(c[2 * i + 1] / max(c[2 * i], 1), 2)} for i, n in enumerate(names)}
-out["inner_pops_dropped"] = c[10]
-out["kernel_ms"] = g.last_kernel_ms()[0]
+out["inner_pops_dropped"] = c[10]; out["cold_pops"] = c[8] >> 32; out["guard"]["iterations"] &= 0xffffffff
+out["max_iterations_of_a_warp"] = c[9]; out["guard"]["lanes"] = 0; out["warps"] = 148 * 3 * 8; out["kernel_ms"] = g.last_kernel_ms()[0]
 print(json.dumps(out))
