@@ -325,9 +325,9 @@ const SwitchName kSwitches[] = {
     {"split_depth", &Switches::split_depth}, {"raster_inline_shade", &Switches::raster_inline_shade}, {"mlaa_scan", &Switches::mlaa_scan},
     {"mlaa_fullscan", &Switches::mlaa_fullscan}, {"mlaa_nobatch", &Switches::mlaa_nobatch},
     {"no_frame_overlap", &Switches::no_frame_overlap}, {"bvh_serial_split", &Switches::bvh_serial_split},
-    {"pool_stats", &Switches::pool_stats}, {"pool_no_scatter", &Switches::pool_no_scatter},
+    {"pool_stats", &Switches::pool_stats}, {"pool_policy", &Switches::pool_policy}, {"pool_no_scatter", &Switches::pool_no_scatter}, {"pool_occ4", &Switches::pool_occ4},
     {"pool_leaf_min", &Switches::pool_leaf_min}, {"pool_sort_min", &Switches::pool_sort_min}, {"pool_shade_min", &Switches::pool_shade_min},
-    {"pool_refill_min", &Switches::pool_refill_min}, {"pool_dry", &Switches::pool_dry}, {"pool_wide_after", &Switches::pool_wide_after},
+    {"pool_refill_min", &Switches::pool_refill_min}, {"pool_low_water", &Switches::pool_low_water}, {"pool_dry", &Switches::pool_dry},
 };
 
 extern "C" {

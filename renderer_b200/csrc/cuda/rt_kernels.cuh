@@ -12,7 +12,7 @@ struct Switches {
     int no_fuse = 0;              // simple configuration through hit records + rt_shade_kernel as well
     int rt_legacy = 0;            // round 1's job pipeline (rt_rootcull_kernel + rt_primary_kernel) instead of rt_pool_kernel
     int no_root_rect = 0;         // no screen rectangle around the root box: every pixel's ray is built
-    int pool_small = 0;           // rt_pool_kernel with 2-entry private stacks: exercises walk_subtree and the wide conversion
+    int pool_small = 0;           // 128-entry pools: exercises the overflow guard of rt_pool_kernel
     int split_depth = -1;         // job pipeline: BVH levels expanded into jobs (0..3; default 2)
     int raster_inline_shade = 0;  // modes 6-8 shade inside the span walk instead of the per-pixel pass
     int mlaa_scan = 0;            // row-scanning MLAA kernels instead of the two-stage path
@@ -20,7 +20,9 @@ struct Switches {
     int mlaa_nobatch = 0;         // MLAA walks load one word per step
     int no_frame_overlap = 0;     // b200r_render_async keeps ray-traced frames on one stream
     int bvh_serial_split = 0;     // BVH build: one thread per node in every level
-    int pool_leaf_min = 0, pool_sort_min = 0, pool_shade_min = 0, pool_refill_min = 0, pool_dry = 0, pool_wide_after = 0;   // rt_pool_kernel thresholds (0 = built-in)
+    int pool_policy = 0;          // rt_pool_kernel: how the inner pool is popped (rt_pool.cu PoolParams)
+    int pool_leaf_min = 0, pool_sort_min = 0, pool_shade_min = 0, pool_refill_min = 0, pool_low_water = 0, pool_dry = 0;   // rt_pool_kernel thresholds (0 = built-in)
+    int pool_occ4 = 0;            // rt_pool_kernel: 4 CTAs per SM (64 registers, 256-entry pools) instead of 3
     int pool_no_scatter = 0;      // rt_pool_kernel: deal whole 8x4 tiles to warps (centre-out) instead of scattered 4-pixel groups
     int pool_stats = 0;           // rt_pool_kernel adds its per-phase iteration / lane counts to the work counters (tools/pool_stats.py)
 };

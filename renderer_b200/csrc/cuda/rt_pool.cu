@@ -1,35 +1,33 @@
-// rt_pool.cu — the ray tracer's hot kernel: BVH traversal with warp-wide work lists in shared memory.
+// rt_pool.cu — the ray tracer's hot kernel: BVH traversal with a warp-wide WORK POOL in shared memory.
 //
 // What it computes is BVH_IntersectTriangles (reference src/Raytracer.cc:183-308) for the primary ray of every pixel and,
 // in the common configuration (one light, no reflections, no AO), the shading of the hit and its shadow ray
 // (Raytrace, reference src/Raytracer.cc:315-505) - the same rays, the same box and triangle arithmetic (rt_common.cuh), the
 // same winner per ray. How the work is scheduled has nothing in common with the reference's one-ray-one-stack loop:
 //
-//   * A warp owns up to 32 rays at a time ("slots": origin, direction, refined reciprocals, best hit so far, a private stack of
-//     deferred subtrees - all in shared memory) and two work lists: the inner nodes and the leaves its rays are standing at.
-//     A list entry is 8 bytes: {leaf flag | slot | node or list index, entry distance of the node's box}.
-//   * Lanes are not tied to rays. An INNER iteration pops up to 32 entries of the node list and each lane advances one ray by
-//     one node: one 64-byte record holds both children's boxes, so the lane does the two slab tests (true IEEE quotients, the
-//     reference's per-axis rules), keeps the farther surviving child on the ray's private stack and puts the nearer one back on
-//     a list - positions come from warp ballots. A LEAF iteration does the same for up to 32 rays standing at leaves
-//     (triangles in list order, then the ray's next subtree is popped from its stack, skipping what its new bound rules out).
-//     Slab tests and triangle tests therefore run in separate, densely populated passes instead of sharing a diverged warp.
-//   * Per ray this is the reference's depth-first walk, nearest child first, with distance pruning: the
-//     closest hit is the minimum of (hitZ, position in the triangle list) over every triangle of every leaf the reference
-//     would reach that can still win - the reference's strict `<` in its list-order visit (src/Raytracer.cc:287-296).
-//   * A ray that has taken many steps (C2's horizon pixels cross hundreds of boxes: 280 dependent steps in round 1's kernel,
-//     the whole frame's critical path) is turned WIDE: its private stack is emptied onto the lists and from then on both
-//     children of its nodes go there, so all its pending subtrees are walked at once by as many lanes as are free; results
-//     merge with one 64-bit atomicMin on the slot's key, a pending count says when the ray is done. The same happens to every
-//     ray with deferred subtrees once the warp runs out of new pixels.
-//   * A finished ray is black, or (FUSED) shaded with both outcomes of the light test and re-armed in place as the SHADOW ray
-//     of its hit, or (generic configurations) appended as a hit record for rt_shade_kernel. Shading is deferred until several
-//     hits wait so that its long arithmetic runs with more than one lane.
-//   * Persistent CTAs (3 per SM x 148), 8 independent warps each - no CTA-wide barrier anywhere. Warps take pixels in scattered
-//     groups of four from the screen rectangle that can contain the model, build the primary rays themselves and test the root
-//     box against kernel arguments; the frame is cleared beforehand, so the 81 % of C2's pixels that miss are never touched.
-//   * Nothing can overflow: a private stack that is full, or lists that are nearly full, make the lane walk that subtree
-//     depth-first on the spot (walk_subtree - also the path of rays outside the shared-reciprocal divide's domain).
+//   * A warp owns up to 32 rays at a time ("slots": origin, direction, refined reciprocals, best hit so far, pending count -
+//     all in shared memory) and ONE pool of pending BVH nodes for all of them. A pool entry is 8 bytes:
+//     {leaf flag | slot | node or list index, entry distance of the node's box}.
+//   * Every iteration the 32 lanes pop the top 32 entries - whichever rays they belong to - and each lane processes one node:
+//     one 64-byte record holds both children's boxes, so a lane does the two slab tests (true IEEE quotients, the reference's
+//     per-axis rules) and pushes the surviving children back, far child first. Positions come from warp ballots; there is
+//     no per-ray stack and no lane is ever tied to a ray. Leaves go to a second pool and are intersected 32 at a time.
+//   * A ray's pending subtrees are therefore walked by as many lanes as the pool can feed: a ray that crosses hundreds of
+//     boxes (C2's horizon pixels: 280 dependent steps in round 1's lane-per-ray kernel, the whole frame's critical path)
+//     finishes in a few dozen iterations, and the lanes never idle behind the longest ray of their warp.
+//   * The closest hit of a ray is the minimum of (hitZ, position in the triangle list) over every triangle of every leaf
+//     the reference would reach - the reference's strict `<` in its list-order visit (src/Raytracer.cc:287-296) - so the order
+//     in which lanes find hits does not matter: one 64-bit atomicMin per improving hit on the slot's key in shared memory.
+//     Subtrees that can no longer win are dropped when pushed and again when popped (distance pruning, see
+//     rt_common.cuh/primary pruning contract in DESIGN.md section 4); shadow rays stop at the first occluder.
+//   * A slot whose pending count reaches zero is resolved: black, or (FUSED) shaded with both outcomes of the light test and
+//     re-armed as the SHADOW ray of its hit, or (generic configurations) appended as a hit record for rt_shade_kernel.
+//     Resolution is deferred until 8 slots wait (or nothing else is left) so the shading code runs with more than one lane.
+//   * Persistent CTAs (3 per SM x 148), 8 independent warps each - no CTA-wide barrier anywhere. Warps pull 8x4-pixel tiles of
+//     the screen rectangle that can contain the model (centre-out), build the primary rays themselves and test the root box
+//     against kernel arguments; the frame is cleared beforehand, so the 81 % of C2's pixels that miss are never touched.
+//   * The pool cannot overflow: when it is nearly full the top 32 entries are walked depth-first by their lanes with a private
+//     stack (same tests, same merges) instead of being expanded.
 #include "rt_common.cuh"
 #include "rt_kernels.cuh"
 
@@ -40,32 +38,35 @@ namespace {
 
 constexpr int POOL_WARPS = 8;            // warps per CTA (independent of each other)
 constexpr int POOL_CTAS_PER_SM = 3;
+constexpr int CAP_L = 128;               // leaf pool: < LEAF_MIN waiting + at most 64 pushed per inner iteration (+ 32 roots)
 // scheduling thresholds (defaults; developer switches pool_* override them for tuning)
-constexpr int LEAF_MIN = 16;             // run a leaf iteration as soon as this many rays stand at leaves
-constexpr int SORT_MIN = 4;              // look at finished slots once this many wait (or the warp is running dry)
-constexpr int SHADE_MIN = 8;             // shade resolved hits once this many wait (or the warp is running dry)
-constexpr int REFILL_MIN = 8;            // take new pixels once this many slots are free
-constexpr int DRY = 16;                  // "running dry": fewer list entries than this
-constexpr int WIDE_AFTER = 48;           // a ray turns wide after this many steps
+constexpr int LEAF_MIN = 32;             // run a leaf iteration as soon as this many leaves wait
+constexpr int SORT_MIN = 8;              // look at finished slots once this many wait (or the warp is running dry)
+constexpr int SHADE_MIN = 12;            // shade resolved hits once this many wait (or the warp is running dry)
+constexpr int REFILL_MIN = 8;            // take new pixels once this many slots are free ...
+constexpr int LOW_WATER = 32;            // ... and fewer than this many hot entries are pending
+constexpr int DRY = 16;                  // "running dry": fewer inner entries than this are pending
 constexpr uint32_t ITEM_LEAF = 0x80000000u;
 constexpr uint32_t ITEM_INDEX_MASK = 0x03FFFFFFu;     // 26 bits: inner record id or list position
 constexpr uint32_t ITEM_REF_MASK = ITEM_LEAF | ITEM_INDEX_MASK;
 constexpr int ITEM_SLOT_SHIFT = 26;
-constexpr uint32_t SP_WIDE = 0xFFu;      // meta & 0xFF: depth of the private stack, or this mark
 constexpr unsigned long long KEY_EMPTY = ((unsigned long long)0x7F7FFFFFu << 32) | 0xFFFFFFFFull;   // (FLT_MAX, no list position)
 
-// Per-warp state in shared memory. DEPTH = entries of a ray's private stack, CAP = entries of each work list.
-template <int DEPTH, int CAP>
-struct __align__(16) WarpState {
-    uint2 hot[CAP];                      // rays standing at inner nodes (+ every pending inner node of the wide rays)
-    uint2 leaf[CAP];                     // rays standing at leaves (+ every pending leaf of the wide rays)
-    uint2 stk[DEPTH][32];                // [depth][slot]: deferred subtrees {ref, entry distance}; one lane per ray at a time -> no bank conflicts
+// Per-warp state in shared memory. The inner-node pool is ONE array with two stacks: HOT entries (the nearer child of the
+// node just processed - the depth-first continuation of its ray) grow up from index 0, COLD entries (the farther child, which
+// the reference's loop would visit after the whole near subtree) grow down from the end. Lanes pop hot entries first and fill
+// up with cold ones, newest first: with many rays in the warp every ray advances depth-first, nearest box first, and what it
+// finds prunes its cold entries before anyone fetches them; with few rays left the spare lanes walk the cold entries of the
+// same rays, which is what keeps a long ray from becoming the frame's critical path.
+template <int CAP_I>
+struct __align__(16) WarpPool {
+    uint2 ipool[CAP_I];                  // {leaf flag | slot | index, entry distance of the node's box}
+    uint2 lpool[CAP_L];                  // pending leaves
     float4 ro[32];                       // slot: ray origin, pruning slack (+inf: never prune; -inf: ray finished, drop its entries)
     float4 rd[32];                       // slot: ray direction
     float4 rr[32];                       // slot: refined reciprocals of the direction, w = bits(triangle to skip): >= 0 marks a SHADOW ray
     unsigned long long key[32];          // slot: (bits(best hitZ) << 32) | list position; shadow slots: (bits(light distance^2) << 32)
-    uint32_t meta[32];                   // slot: [7:0] private stack depth or SP_WIDE, [31:8] steps taken
-    int pend[32];                        // wide slots: list entries not yet processed
+    int pend[32];                        // slot: pool entries not yet processed
     uint32_t pix[32];                    // slot: (packed row << 16) | x
     uint32_t lit[32], shd[32];           // shadow slots: the two possible pixel words
 };
@@ -141,9 +142,9 @@ __device__ __forceinline__ bool intersect_leaf(const DeviceScene& sc, const V3& 
     }
 }
 
-// Cold path: one lane walks a whole subtree depth-first with a stack of its own - the reference's loop with near-first order
+// Cold path: one lane walks a whole subtree depth-first with a private stack - the reference's own loop with near-first order
 // and pruning. Used for rays outside the shared-reciprocal domain (a zero direction component: they take the reference's
-// `dir == 0` rule, ray_box<false>) and whenever a private stack or a work list is full. Results go where the lists' lanes put theirs.
+// `dir == 0` rule, ray_box<false>) and when a pool is about to overflow. Results go where the pooled lanes put theirs.
 __device__ __noinline__ void walk_subtree(const DeviceScene& sc, const RayPrep rp, const int avoid, const V3 lightPos, uint32_t cur, float tcur,
                                           unsigned long long* key, const volatile float* slackWord)
 {
@@ -163,7 +164,7 @@ __device__ __noinline__ void walk_subtree(const DeviceScene& sc, const RayPrep r
                 }
                 if (bestK < k0) atomicMin(key, bestK);
             } else {
-                const float4* rec = sc.wnodes + 4 * (size_t)(cur & ITEM_INDEX_MASK);
+                const float4* rec = sc.wnodes + 4 * (size_t)cur;
                 const float4 bx = __ldg(rec + 0), by = __ldg(rec + 1), bz = __ldg(rec + 2), rf = __ldg(rec + 3);
                 const uint32_t L = __float_as_uint(rf.x), R = __float_as_uint(rf.y);
                 bool hitL, hitR; float tL = tcur, tR = tcur;
@@ -191,128 +192,81 @@ __device__ __noinline__ void walk_subtree(const DeviceScene& sc, const RayPrep r
     }
 }
 
+// How pixels are dealt to warps and how the inner pool is popped (PoolParams.policy, developer switch pool_policy):
+//   0  hot entries first, spare lanes take cold ones (depth-first per ray while the warp has enough rays)
+//   1  one stack: the farther child is pushed under the nearer one and both are popped as they come (breadth grows fast)
+//   2  like 0, but up to 8 lanes always go to cold entries
+//   3  one stack, each lane's farther child directly under its nearer one: a node's two children are popped together,
+//      a ray's pending subtrees spread over the lanes at once (shortest chains of dependent iterations, weakest pruning)
 struct PoolParams {
     int4 tiles;                     // first tile column / row, tile columns / rows of the screen rectangle that can contain the model
-    int prune;
-    int leafMin, sortMin, shadeMin, refillMin, dry, wideAfter;
+    int prune, policy;
+    int leafMin, sortMin, shadeMin, refillMin, lowWater, dry;
     unsigned scatterMul;            // 0: tiles are dealt in centre-out order, 32 neighbouring pixels per grab; else: 4-pixel groups
     unsigned nGroups, groupsPerRow; //    are dealt in the order (q * scatterMul) mod nGroups, so every warp holds a cross-section
     unsigned long long scatterInv;  //    of the frame instead of one tile (floor(2^64 / nGroups), for the modulo)
 };
 
 // STATS (developer switch pool_stats): per-phase iteration / lane counts are added to DeviceCounters (tools/pool_stats.py).
-template <bool FUSED, int DEPTH, int CAP, bool STATS = false>
-__global__ void __launch_bounds__(POOL_WARPS * 32, POOL_CTAS_PER_SM)
+template <bool FUSED, int CAP_I, bool STATS = false, int CTAS = POOL_CTAS_PER_SM>
+__global__ void __launch_bounds__(POOL_WARPS * 32, CTAS)
 rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsigned* __restrict__ pixelCounter, PoolParams pp,
                HitRecord* __restrict__ hits, unsigned* __restrict__ hitCount, DeviceCounters* __restrict__ stats)
 {
-    static_assert(DEPTH >= 1 && DEPTH <= 32 && CAP >= 160, "list capacity: see the room checks (`tight`, conversion, shading, refill)");
-    unsigned st_it[4] = {0, 0, 0, 0}, st_ln[4] = {0, 0, 0, 0}, st_conv = 0, st_walk = 0, st_wide = 0;   // inner, leaf, shade, refill
+    const int4 tiles = pp.tiles;
+    const int prune = pp.prune, policy = pp.policy;
+    const int LEAF_MIN = pp.leafMin, SORT_MIN = pp.sortMin, SHADE_MIN = pp.shadeMin, REFILL_MIN = pp.refillMin, LOW_WATER = pp.lowWater, DRY = pp.dry;
+    unsigned st_it[5] = {0, 0, 0, 0, 0}, st_ln[5] = {0, 0, 0, 0, 0}, st_drop = 0, st_cold = 0;   // inner, leaf, resolve, refill, guard
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    using State = WarpState<DEPTH, CAP>;
-    State& P = reinterpret_cast<State*>(smem_raw)[threadIdx.x >> 5];
+    using Pool = WarpPool<CAP_I>;
+    Pool& P = reinterpret_cast<Pool*>(smem_raw)[threadIdx.x >> 5];
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt = (1u << lane) - 1u;
     const unsigned FULL = 0xffffffffu;
     const V3 eye = mkv3(fp.eye[0], fp.eye[1], fp.eye[2]);
     const V3 lightPos = mkv3(fp.light_pos[0][0], fp.light_pos[0][1], fp.light_pos[0][2]);
-    const int4 tiles = pp.tiles;
     const int tx0 = tiles.x, ty0 = tiles.y, ntx = tiles.z, nty = tiles.w;
     const unsigned total = (unsigned)(ntx * nty) * 32u;
     const float INF = __int_as_float(0x7f800000);
-    const int LEAF_MIN = pp.leafMin, SORT_MIN = pp.sortMin, SHADE_MIN = pp.shadeMin, REFILL_MIN = pp.refillMin, DRY = pp.dry;
-    const unsigned WIDE_AFTER = (unsigned)pp.wideAfter;
 
     // warp-uniform bookkeeping
-    int hcount = 0, lcount = 0;                     // entries of the two lists
-    unsigned freeMask = FULL, doneMask = 0u, shadeMask = 0u, convMask = 0u;   // slots: free / finished / hit waiting for shading / to be turned wide
+    int hcount = 0, ccount = 0, lcount = 0;         // hot / cold inner entries, leaves
+    unsigned freeMask = FULL, doneMask = 0u, shadeMask = 0u;       // slots: free / finished, not looked at yet / resolved hits waiting to be shaded
     bool exhausted = (total == 0u);
 
-    // One ray has been advanced by its lane (inner or leaf iteration): what is left to do for it. Ordinary ray: `sp`/`steps` are its
-    // private stack depth and step count; if it has no node to go on with (!go) its stack is popped, skipping subtrees its bound
-    // rules out. Returns true when the ray is finished.
-    auto next_of_ordinary = [&](uint32_t slot, uint32_t sp, uint32_t steps, float slack, float best, bool& go, uint32_t& ref, float& t,
-                                bool allWide, bool& wantWide) -> bool {
-        while (!go && sp > 0u) {
-            --sp;
-            const uint2 e = P.stk[sp][slot];
-            if (pruned(__uint_as_float(e.y), slack, best)) continue;
-            ref = e.x; t = __uint_as_float(e.y); go = true;
-        }
-        steps++;
-        wantWide = go && sp > 0u && (steps >= WIDE_AFTER || allWide);
-        P.meta[slot] = sp | (steps << 8);
-        return !go;
-    };
-
     for (;;) {
-        // Room in the lists: an inner iteration of wide rays may push 64 entries onto each list, a leaf iteration / shading / a refill 32,
-        // a conversion DEPTH. `tight`: wide rays stop spreading (their farther subtrees are walked on the spot) until there is room again.
-        const bool tight = CAP - hcount < 72 || CAP - lcount < 72;
-        const bool room32 = CAP - hcount >= 40 && CAP - lcount >= 40;
-        // ------------------------------------------------------------------ rays that took many steps (or all, once the warp runs out of
-        // pixels): the private stack goes onto the lists, from now on every pending subtree of the ray is walked in parallel
-        if (convMask) {
-            while (convMask) {
-                const uint32_t slot = (uint32_t)__ffs(convMask) - 1u;
-                convMask &= convMask - 1u;
-                const uint32_t sp = P.meta[slot] & 0xFFu;
-                if (sp == SP_WIDE || sp == 0u || CAP - hcount < 96 || CAP - lcount < 96) continue;
-                bool mine = lane < sp; uint2 e = make_uint2(0u, 0u);
-                if (mine) { e = P.stk[lane][slot]; e.x = make_item(e.x, slot); }
-                const unsigned bI = __ballot_sync(FULL, mine && !(e.x & ITEM_LEAF)), bL = __ballot_sync(FULL, mine && (e.x & ITEM_LEAF));
-                if (mine) { if (e.x & ITEM_LEAF) P.leaf[lcount + __popc(bL & lt)] = e; else P.hot[hcount + __popc(bI & lt)] = e; }
-                hcount += __popc(bI); lcount += __popc(bL);
-                if (lane == 0) { P.pend[slot] = (int)sp + 1; P.meta[slot] = SP_WIDE; }     // + 1: the node the ray is standing at
-                if (STATS) st_conv++;
-            }
-            __syncwarp();
-            continue;
-        }
-        // ------------------------------------------------------------------ leaves
-        if (lcount >= LEAF_MIN || (lcount > 0 && hcount == 0)) {
+        // ------------------------------------------------------------------ leaves, 32 at a time
+        if (lcount >= LEAF_MIN || (lcount > 0 && hcount + ccount == 0)) {
             const int n = min(32, lcount);
             lcount -= n;
             if (STATS) { st_it[1]++; st_ln[1] += n; }
-            bool fin = false, go = false, wantWide = false; uint32_t slot = 0, ref = 0; float t = 0.f;
-            const bool allWide = exhausted && hcount + lcount < DRY;
+            bool fin = false; uint32_t slot = 0;
             if ((int)lane < n) {
-                const uint2 it = P.leaf[lcount + n - 1 - (int)lane];
+                const uint2 it = P.lpool[lcount + n - 1 - (int)lane];
                 slot = (it.x >> ITEM_SLOT_SHIFT) & 31u;
                 const float4 ro = P.ro[slot];
-                const uint32_t meta = P.meta[slot];
-                const bool wide = (meta & 0xFFu) == SP_WIDE;
                 const unsigned long long k0 = P.key[slot];
-                float best = __uint_as_float((uint32_t)(k0 >> 32));
-                bool occ = false;
+                const float best = __uint_as_float((uint32_t)(k0 >> 32));
                 if (!pruned(__uint_as_float(it.y), ro.w, best)) {
                     const float4 rd = P.rd[slot];
                     unsigned long long bestK = k0;
-                    occ = intersect_leaf(sc, mkv3(ro.x, ro.y, ro.z), mkv3(rd.x, rd.y, rd.z), it.x & ITEM_INDEX_MASK,
-                                         __float_as_int(P.rr[slot].w), lightPos, best, bestK);
+                    const bool occ = intersect_leaf(sc, mkv3(ro.x, ro.y, ro.z), mkv3(rd.x, rd.y, rd.z), it.x & ITEM_INDEX_MASK,
+                                                    __float_as_int(P.rr[slot].w), lightPos, best, bestK);
                     if (occ) P.ro[slot].w = -INF;
-                    else if (bestK < k0) {
-                        if (wide) atomicMin(&P.key[slot], bestK); else P.key[slot] = bestK;
-                        best = __uint_as_float((uint32_t)(bestK >> 32));
-                    }
+                    else if (bestK < k0) atomicMin(&P.key[slot], bestK);
                 }
-                if (wide) fin = atomicSub(&P.pend[slot], 1) == 1;
-                else fin = next_of_ordinary(slot, occ ? 0u : (meta & 0xFFu), meta >> 8, ro.w, best, go, ref, t, allWide, wantWide);
+                fin = atomicSub(&P.pend[slot], 1) == 1;
             }
-            const unsigned bI = __ballot_sync(FULL, go && !(ref & REF_LEAF)), bL = __ballot_sync(FULL, go && (ref & REF_LEAF));
-            if (go) {
-                const uint2 item = make_uint2(make_item(ref, slot), __float_as_uint(t));
-                if (ref & REF_LEAF) P.leaf[lcount + __popc(bL & lt)] = item; else P.hot[hcount + __popc(bI & lt)] = item;
-            }
-            hcount += __popc(bI); lcount += __popc(bL);
             doneMask |= __reduce_or_sync(FULL, fin ? (1u << slot) : 0u);
-            convMask |= __reduce_or_sync(FULL, wantWide ? (1u << slot) : 0u);
             __syncwarp();
             continue;
         }
         // ------------------------------------------------------------------ finished slots: shadow rays write their pixel, primary rays
         // that pierced nothing are done (the frame was cleared to black), resolved hits queue up for shading
-        const bool dry = hcount + lcount < DRY;
+        // (every branch that pushes checks the room left in the inner pool: an inner iteration needs 64 free entries - each of
+        // its <= 32 lanes may push two - or it runs as the overflow guard; shading / refilling push at most 32)
+        const int room = CAP_I - (hcount + ccount);
+        const bool dry = hcount + ccount < DRY;
         const int ndone = __popc(doneMask);
         if (ndone >= SORT_MIN || (ndone > 0 && dry)) {
             bool freed = false, hit = false; uint32_t slot = 0;
@@ -332,7 +286,7 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
         }
         // ------------------------------------------------------------------ resolved hits: shade + shadow ray / hit record
         const int nshade = __popc(shadeMask);
-        if ((nshade >= SHADE_MIN || (nshade > 0 && dry)) && room32) {
+        if ((nshade >= SHADE_MIN || (nshade > 0 && dry)) && room >= 32) {
             if (STATS) { st_it[2]++; st_ln[2] += nshade; }
             bool freed = false, arm = false; uint32_t slot = 0;
             bool record = false; int tri = -1; V3 hitp = eye; float kAB = 0.f, kBC = 0.f, kCA = 0.f;
@@ -358,14 +312,10 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
                         if (!enter) out[o] = pixLit;
                         else {
                             P.ro[slot] = make_float4(hitp.x, hitp.y, hitp.z, INF);         // any-hit ray: no distance pruning
-                            P.rd[slot] = make_float4(sdir.x, sdir.y, sdir.z, 0.f);
+                            P.rd[slot] = make_float4(sdir.x, sdir.y, sdir.z, rp.fast ? 0.f : 1.f);
                             P.rr[slot] = make_float4(rp.r.x, rp.r.y, rp.r.z, __int_as_float(tri));
                             P.key[slot] = (unsigned long long)__float_as_uint(ldsq) << 32;
-                            if (rp.fast) { P.meta[slot] = 0u; P.lit[slot] = pixLit; P.shd[slot] = pixShadow; freed = false; arm = true; }
-                            else {          // outside the shared-reciprocal domain: walked here, by this lane
-                                walk_subtree(sc, rp, tri, lightPos, sc.root_ref, -FLT_MAX, &P.key[slot], &P.ro[slot].w);
-                                out[o] = (P.ro[slot].w == -INF) ? pixShadow : pixLit;
-                            }
+                            P.pend[slot] = 1; P.lit[slot] = pixLit; P.shd[slot] = pixShadow; freed = false; arm = true;
                         }
                     }
                 } else record = true;
@@ -374,8 +324,8 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
                 const unsigned am = __ballot_sync(FULL, arm);
                 if (am) {
                     const uint2 item = make_uint2(make_item(sc.root_ref, slot), __float_as_uint(-FLT_MAX));
-                    if (sc.root_ref & REF_LEAF) { if (arm) P.leaf[lcount + __popc(am & lt)] = item; lcount += __popc(am); }
-                    else { if (arm) P.hot[hcount + __popc(am & lt)] = item; hcount += __popc(am); }
+                    if (sc.root_ref & REF_LEAF) { if (arm) P.lpool[lcount + __popc(am & lt)] = item; lcount += __popc(am); }
+                    else { if (arm) P.ipool[hcount + __popc(am & lt)] = item; hcount += __popc(am); }
                 }
             } else {
                 const unsigned hm = __ballot_sync(FULL, record);
@@ -396,7 +346,7 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
             continue;
         }
         // ------------------------------------------------------------------ new pixels into free slots
-        if (!exhausted && room32 && (__popc(freeMask) >= REFILL_MIN || hcount + lcount == 0)) {
+        if (!exhausted && hcount < LOW_WATER && room >= 32 && (__popc(freeMask) >= REFILL_MIN || hcount + ccount == 0)) {
             const int nfree = __popc(freeMask);
             unsigned base = 0;
             if (lane == 0) base = atomicAdd(pixelCounter, (unsigned)nfree);
@@ -429,31 +379,27 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
             }
             const unsigned em = __ballot_sync(FULL, enter);
             if (STATS) { st_it[3]++; st_ln[3] += __popc(em); }
-            uint32_t slot = 0; bool walked = false;
+            uint32_t slot = 0; const bool walked = false;
             if (enter) {
                 slot = __fns(freeMask, 0u, __popc(em & lt) + 1);
                 float slack = INF;
-                if (pp.prune) {
+                if (prune) {
                     // 1/|d| per axis (IEEE divide; +inf for a zero component switches pruning off for this ray)
                     const float m = fmaxf(fmaxf(1.0f / fabsf(rp.d.x), 1.0f / fabsf(rp.d.y)), 1.0f / fabsf(rp.d.z));
                     slack = 1e-4f * m + 1e-4f;
                 }
                 P.ro[slot] = make_float4(rp.o.x, rp.o.y, rp.o.z, slack);
-                P.rd[slot] = make_float4(rp.d.x, rp.d.y, rp.d.z, 0.f);
+                P.rd[slot] = make_float4(rp.d.x, rp.d.y, rp.d.z, rp.fast ? 0.f : 1.f);
                 P.rr[slot] = make_float4(rp.r.x, rp.r.y, rp.r.z, __int_as_float(-1));
                 P.key[slot] = KEY_EMPTY;
                 P.pix[slot] = ((uint32_t)r << 16) | (uint32_t)x;
-                P.meta[slot] = 0u;
-                if (!rp.fast) {     // outside the shared-reciprocal domain: walked here, by this lane, then resolved like any other
-                    walk_subtree(sc, rp, -1, lightPos, sc.root_ref, -FLT_MAX, &P.key[slot], &P.ro[slot].w);
-                    walked = true;
-                }
+                P.pend[slot] = 1;
             }
             const unsigned pm = __ballot_sync(FULL, enter && !walked);
             if (enter && !walked) {
                 const uint2 item = make_uint2(make_item(sc.root_ref, slot), __float_as_uint(-FLT_MAX));
-                if (sc.root_ref & REF_LEAF) P.leaf[lcount + __popc(pm & lt)] = item;
-                else P.hot[hcount + __popc(pm & lt)] = item;
+                if (sc.root_ref & REF_LEAF) P.lpool[lcount + __popc(pm & lt)] = item;
+                else P.ipool[hcount + __popc(pm & lt)] = item;
             }
             if (sc.root_ref & REF_LEAF) lcount += __popc(pm); else hcount += __popc(pm);
             freeMask &= ~__reduce_or_sync(FULL, enter ? (1u << slot) : 0u);
@@ -461,23 +407,40 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
             __syncwarp();
             continue;
         }
-        if (hcount == 0) break;            // nothing pending, nothing waiting, no pixels left
+        if (hcount + ccount == 0) break;            // nothing pending, nothing waiting, no pixels left
 
-        // ------------------------------------------------------------------ inner nodes
-        const int n = min(32, hcount);
-        hcount -= n;
-        if (STATS) { st_it[0]++; st_ln[0] += n; }
-        bool fin = false, go = false, goFar = false, wantWide = false;
-        uint32_t slot = 0, ref = 0, refFar = 0; float t = 0.f, tFar = 0.f;
-        const bool allWide = exhausted && hcount + lcount < DRY;
-        if ((int)lane < n) {
-            const uint2 it = P.hot[hcount + n - 1 - (int)lane];
-            slot = (it.x >> ITEM_SLOT_SHIFT) & 31u;
+        // ------------------------------------------------------------------ inner nodes, 32 at a time: hot entries first, then cold
+        int nh = min(32, hcount), nc = min(32 - nh, ccount);
+        if (policy == 2 && nc < 8 && ccount > nc) { nc = min(8, ccount); nh = min(nh, 32 - nc); }
+        const bool guard = room < 64;
+        uint2 it = make_uint2(0u, 0u);
+        const bool have = (int)lane < nh + nc;
+        if ((int)lane < nh) it = P.ipool[hcount - 1 - (int)lane];
+        else if (have) it = P.ipool[CAP_I - ccount + ((int)lane - nh)];
+        hcount -= nh; ccount -= nc;
+        bool fin = false;
+        const uint32_t slot = (it.x >> ITEM_SLOT_SHIFT) & 31u;
+        if (guard) {
+            // (overflow guard) the pool is nearly full: each lane walks its entry's whole subtree itself instead of expanding it
+            if (STATS) { st_it[4]++; st_ln[4] += nh + nc; }
+            if (have) {
+                const float4 ro = P.ro[slot], rd = P.rd[slot], rr = P.rr[slot];
+                RayPrep rp; rp.o = mkv3(ro.x, ro.y, ro.z); rp.d = mkv3(rd.x, rd.y, rd.z); rp.r = mkv3(rr.x, rr.y, rr.z); rp.fast = rd.w == 0.f;
+                walk_subtree(sc, rp, __float_as_int(rr.w), lightPos, it.x & ITEM_REF_MASK, __uint_as_float(it.y), &P.key[slot], &P.ro[slot].w);
+                fin = atomicSub(&P.pend[slot], 1) == 1;
+            }
+            doneMask |= __reduce_or_sync(FULL, fin ? (1u << slot) : 0u);
+            __syncwarp();
+            continue;
+        }
+        if (STATS) { st_it[0]++; st_ln[0] += nh + nc; st_cold += nc; }
+        uint32_t cN = 0, cF = 0; float tN = 0.f, tF = 0.f;          // surviving children: the nearer one, the farther one
+        bool pN = false, pF = false;
+        if (have) {
             const float4 ro = P.ro[slot];
-            const uint32_t meta = P.meta[slot];
-            const bool wide = (meta & 0xFFu) == SP_WIDE;
             const float best = __uint_as_float(reinterpret_cast<const uint32_t*>(&P.key[slot])[1]);
             const float tHere = __uint_as_float(it.y);
+            int delta = -1;
             if (!pruned(tHere, ro.w, best)) {
                 const float4 rd = P.rd[slot], rr = P.rr[slot];
                 const float4* rec = sc.wnodes + 4 * (size_t)(it.x & ITEM_INDEX_MASK);
@@ -485,9 +448,15 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
                 const uint32_t L = __float_as_uint(rf.x), R = __float_as_uint(rf.y);
                 // both boxes, unconditionally (straight-line code). A LEAF child has no box test in the reference
                 // (src/Raytracer.cc:224-229): it survives unless empty; its box only supplies a tighter entry distance.
-                float tL, tR;
-                bool hitL = box_fast(ro, rd, rr, bx.x, bx.y, by.x, by.y, bz.x, bz.y, tL);
-                bool hitR = box_fast(ro, rd, rr, bx.z, bx.w, by.z, by.w, bz.z, bz.w, tR);
+                float tL, tR; bool hitL, hitR;
+                if (rd.w == 0.f) {
+                    hitL = box_fast(ro, rd, rr, bx.x, bx.y, by.x, by.y, bz.x, bz.y, tL);
+                    hitR = box_fast(ro, rd, rr, bx.z, bx.w, by.z, by.w, bz.z, bz.w, tR);
+                } else {            // a ray outside the shared-reciprocal domain (e.g. a zero direction component): the reference's own rules
+                    RayPrep rp; rp.o = mkv3(ro.x, ro.y, ro.z); rp.d = mkv3(rd.x, rd.y, rd.z); rp.r = rp.d; rp.fast = false;
+                    hitL = ray_box<false>(rp, bx.x, bx.y, by.x, by.y, bz.x, bz.y, &tL);
+                    hitR = ray_box<false>(rp, bx.z, bx.w, by.z, by.w, bz.z, bz.w, &tR);
+                }
                 if (L & REF_LEAF) { if (!hitL) tL = tHere; hitL = (L != REF_EMPTY); }
                 if (R & REF_LEAF) { if (!hitR) tR = tHere; hitR = (R != REF_EMPTY); }
                 const uint32_t unprunable = __float_as_uint(rf.z);        // bit0/bit1: L/R subtree holds a triangle that failed the upload check
@@ -496,65 +465,44 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
                 if (hitL && pruned(tL, ro.w, best)) hitL = false;
                 if (hitR && pruned(tR, ro.w, best)) hitR = false;
                 const bool rFirst = hitR && (!hitL || tR < tL);
-                ref = rFirst ? R : L; t = rFirst ? tR : tL; go = hitL || hitR;
-                refFar = rFirst ? L : R; tFar = rFirst ? tL : tR; goFar = hitL && hitR;
-            }
-            if (wide) {
-                if (STATS) st_wide++;
-                if (tight && goFar) {           // no room to spread: the farther subtree is walked here and now
-                    RayPrep rp; rp.o = mkv3(ro.x, ro.y, ro.z);
-                    const float4 rd = P.rd[slot], rr = P.rr[slot];
-                    rp.d = mkv3(rd.x, rd.y, rd.z); rp.r = mkv3(rr.x, rr.y, rr.z); rp.fast = true;
-                    walk_subtree(sc, rp, __float_as_int(rr.w), lightPos, refFar, tFar, &P.key[slot], &P.ro[slot].w);
-                    goFar = false;
-                    if (STATS) st_walk++;
-                }
-                const int delta = -1 + (go ? 1 : 0) + (goFar ? 1 : 0);
-                if (delta != 0) fin = (atomicAdd(&P.pend[slot], delta) + delta) == 0;
-            } else {
-                uint32_t sp = meta & 0xFFu;
-                if (goFar) {
-                    if (sp < (uint32_t)DEPTH) { P.stk[sp][slot] = make_uint2(refFar, __float_as_uint(tFar)); sp++; }
-                    else {                      // private stack full: the farther subtree is walked here and now
-                        RayPrep rp; rp.o = mkv3(ro.x, ro.y, ro.z);
-                        const float4 rd = P.rd[slot], rr = P.rr[slot];
-                        rp.d = mkv3(rd.x, rd.y, rd.z); rp.r = mkv3(rr.x, rr.y, rr.z); rp.fast = true;
-                        walk_subtree(sc, rp, __float_as_int(rr.w), lightPos, refFar, tFar, &P.key[slot], &P.ro[slot].w);
-                        if (STATS) st_walk++;
-                    }
-                    goFar = false;
-                }
-                const float bestNow = __uint_as_float(reinterpret_cast<const volatile uint32_t*>(&P.key[slot])[1]);
-                fin = next_of_ordinary(slot, sp, meta >> 8, P.ro[slot].w, bestNow, go, ref, t, allWide, wantWide);
-            }
+                cN = rFirst ? R : L; tN = rFirst ? tR : tL; pN = hitL || hitR;
+                cF = rFirst ? L : R; tF = rFirst ? tL : tR; pF = hitL && hitR;
+                delta += (pN ? 1 : 0) + (pF ? 1 : 0);
+            } else if (STATS) st_drop++;
+            if (delta != 0) fin = (atomicAdd(&P.pend[slot], delta) + delta) == 0;
         }
         {
-            const unsigned bI = __ballot_sync(FULL, go && !(ref & REF_LEAF)), bL = __ballot_sync(FULL, go && (ref & REF_LEAF));
-            if (go) {
-                const uint2 item = make_uint2(make_item(ref, slot), __float_as_uint(t));
-                if (ref & REF_LEAF) P.leaf[lcount + __popc(bL & lt)] = item; else P.hot[hcount + __popc(bI & lt)] = item;
+            const bool oneStack = policy == 1 || policy == 3;
+            const bool hN = pN && !(cN & REF_LEAF), hF = pF && !(cF & REF_LEAF);      // inner children: near -> hot, far -> cold
+            const bool lN = pN && (cN & REF_LEAF), lF = pF && (cF & REF_LEAF);        // leaves: straight to the leaf pool
+            const unsigned bH = __ballot_sync(FULL, hN), bC = __ballot_sync(FULL, hF);
+            const unsigned bL0 = __ballot_sync(FULL, lF), bL1 = __ballot_sync(FULL, lN);
+            if (policy == 3) {          // one stack, every lane's far child directly under its near child: both are popped together
+                const int io = hcount + __popc(bC & lt) + __popc(bH & lt);
+                if (hF) P.ipool[io] = make_uint2(make_item(cF, slot), __float_as_uint(tF));
+                if (hN) P.ipool[io + (hF ? 1 : 0)] = make_uint2(make_item(cN, slot), __float_as_uint(tN));
+            } else if (oneStack) {      // far children first, the near ones on top of them
+                if (hF) P.ipool[hcount + __popc(bC & lt)] = make_uint2(make_item(cF, slot), __float_as_uint(tF));
+                if (hN) P.ipool[hcount + __popc(bC) + __popc(bH & lt)] = make_uint2(make_item(cN, slot), __float_as_uint(tN));
+            } else {
+                if (hN) P.ipool[hcount + __popc(bH & lt)] = make_uint2(make_item(cN, slot), __float_as_uint(tN));
+                if (hF) P.ipool[CAP_I - 1 - ccount - __popc(bC & lt)] = make_uint2(make_item(cF, slot), __float_as_uint(tF));
             }
-            hcount += __popc(bI); lcount += __popc(bL);
-            if (__any_sync(FULL, goFar)) {          // wide rays only: the farther child goes onto the lists as well
-                const unsigned cI = __ballot_sync(FULL, goFar && !(refFar & REF_LEAF)), cL = __ballot_sync(FULL, goFar && (refFar & REF_LEAF));
-                if (goFar) {
-                    const uint2 item = make_uint2(make_item(refFar, slot), __float_as_uint(tFar));
-                    if (refFar & REF_LEAF) P.leaf[lcount + __popc(cL & lt)] = item; else P.hot[hcount + __popc(cI & lt)] = item;
-                }
-                hcount += __popc(cI); lcount += __popc(cL);
-            }
+            if (lF) P.lpool[lcount + __popc(bL0 & lt)] = make_uint2(make_item(cF, slot), __float_as_uint(tF));
+            if (lN) P.lpool[lcount + __popc(bL0) + __popc(bL1 & lt)] = make_uint2(make_item(cN, slot), __float_as_uint(tN));
+            hcount += __popc(bH) + (oneStack ? __popc(bC) : 0); ccount += oneStack ? 0 : __popc(bC);
+            lcount += __popc(bL0) + __popc(bL1);
         }
         doneMask |= __reduce_or_sync(FULL, fin ? (1u << slot) : 0u);
-        convMask |= __reduce_or_sync(FULL, wantWide ? (1u << slot) : 0u);
         __syncwarp();
     }
     if (STATS) {
-        st_walk = __reduce_add_sync(FULL, st_walk); st_wide = __reduce_add_sync(FULL, st_wide);
+        st_drop = __reduce_add_sync(FULL, st_drop);
         if (lane == 0) {
-            for (int i = 0; i < 4; i++) { atomicAdd(&stats->v[2 * i], (unsigned long long)st_it[i]); atomicAdd(&stats->v[2 * i + 1], (unsigned long long)st_ln[i]); }
-            atomicAdd(&stats->v[8], ((unsigned long long)st_walk << 32) | st_conv);      // subtrees walked on the spot | rays turned wide
-            atomicMax(&stats->v[9], (unsigned long long)(st_it[0] + st_it[1] + st_it[2] + st_it[3]));   // most iterations of any warp
-            atomicAdd(&stats->v[10], (unsigned long long)st_wide);                       // inner steps of wide rays
+            for (int i = 0; i < 5; i++) { atomicAdd(&stats->v[2 * i], (unsigned long long)st_it[i]); atomicAdd(&stats->v[2 * i + 1], (unsigned long long)st_ln[i]); }
+            atomicAdd(&stats->v[10], (unsigned long long)st_drop);
+            atomicAdd(&stats->v[8], (unsigned long long)st_cold << 32);      // packed beside the guard iterations
+            atomicMax(&stats->v[9], (unsigned long long)(st_it[0] + st_it[1] + st_it[2] + st_it[3] + st_it[4]));   // most iterations of any warp
         }
     }
 }
@@ -583,13 +531,15 @@ bool pool_supported(const DeviceScene& sc)
 cudaError_t rt_pool_configure()
 {
     cudaError_t e = cudaSuccess;
-    const int big = (int)(sizeof(WarpState<16, 160>) * POOL_WARPS), small = (int)(sizeof(WarpState<2, 160>) * POOL_WARPS);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<true, 16, 160>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<false, 16, 160>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<true, 16, 160, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<false, 16, 160, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<true, 2, 160>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<false, 2, 160>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+    const int big = (int)(sizeof(WarpPool<512>) * POOL_WARPS), small = (int)(sizeof(WarpPool<128>) * POOL_WARPS);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<true, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<false, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<true, 256, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpPool<256>) * POOL_WARPS));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<false, 256, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpPool<256>) * POOL_WARPS));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
     return e;
 }
 
@@ -604,10 +554,12 @@ cudaError_t launch_rt_pool(const DeviceScene& sc, const FrameParams& fp, uint32_
     pp.tiles = tile_rect(fp, bounds);
     if (pp.tiles.z <= 0 || pp.tiles.w <= 0) return cudaSuccess;
     pp.prune = prune ? 1 : 0;
+    pp.policy = sw.pool_policy;
     pp.leafMin = sw.pool_leaf_min > 0 ? sw.pool_leaf_min : LEAF_MIN; pp.sortMin = sw.pool_sort_min > 0 ? sw.pool_sort_min : SORT_MIN;
     pp.shadeMin = sw.pool_shade_min > 0 ? sw.pool_shade_min : SHADE_MIN; pp.refillMin = sw.pool_refill_min > 0 ? sw.pool_refill_min : REFILL_MIN;
-    pp.dry = sw.pool_dry > 0 ? sw.pool_dry : DRY; pp.wideAfter = sw.pool_wide_after > 0 ? sw.pool_wide_after : WIDE_AFTER;
-    if (pp.leafMin > 32) pp.leafMin = 32;
+    pp.lowWater = sw.pool_low_water > 0 ? sw.pool_low_water : LOW_WATER; pp.dry = sw.pool_dry > 0 ? sw.pool_dry : DRY;
+    if (pp.leafMin > 32) pp.leafMin = 32;             // the leaf pool holds < leafMin + 64 + 32 entries
+    if (pp.lowWater > 64) pp.lowWater = 64;
     pp.nGroups = (unsigned)pp.tiles.z * 2u * (unsigned)pp.tiles.w * 4u;
     pp.groupsPerRow = (unsigned)pp.tiles.z * 2u;
     pp.scatterMul = 0; pp.scatterInv = 0;
@@ -621,11 +573,14 @@ cudaError_t launch_rt_pool(const DeviceScene& sc, const FrameParams& fp, uint32_
     }
     using K = void (*)(DeviceScene, FrameParams, uint32_t*, unsigned*, PoolParams, HitRecord*, unsigned*, DeviceCounters*);
     K k; size_t smem;
-    // pool_small: 2-entry private stacks, so the parity tests exercise walk_subtree and the wide conversion all the time
-    if (sw.pool_small) { k = fused ? rt_pool_kernel<true, 2, 160> : rt_pool_kernel<false, 2, 160>; smem = sizeof(WarpState<2, 160>) * POOL_WARPS; }
-    else { k = fused ? rt_pool_kernel<true, 16, 160> : rt_pool_kernel<false, 16, 160>; smem = sizeof(WarpState<16, 160>) * POOL_WARPS; }
-    if (stats && !sw.pool_small) k = fused ? rt_pool_kernel<true, 16, 160, true> : rt_pool_kernel<false, 16, 160, true>;
-    int grid = numSMs * POOL_CTAS_PER_SM;
+    if (sw.pool_small) { k = fused ? rt_pool_kernel<true, 128> : rt_pool_kernel<false, 128>; smem = sizeof(WarpPool<128>) * POOL_WARPS; }
+    else { k = fused ? rt_pool_kernel<true, 512> : rt_pool_kernel<false, 512>; smem = sizeof(WarpPool<512>) * POOL_WARPS; }
+    if (stats && !sw.pool_small) k = fused ? rt_pool_kernel<true, 512, true> : rt_pool_kernel<false, 512, true>;
+    int ctas = POOL_CTAS_PER_SM;
+    if (sw.pool_occ4 && !sw.pool_small && !stats) {      // 4 CTAs per SM: 64 registers per thread, 256-entry pools
+        k = fused ? rt_pool_kernel<true, 256, false, 4> : rt_pool_kernel<false, 256, false, 4>; smem = sizeof(WarpPool<256>) * POOL_WARPS; ctas = 4;
+    }
+    int grid = numSMs * ctas;
     const int needed = (pp.tiles.z * pp.tiles.w + POOL_WARPS - 1) / POOL_WARPS;       // one tile per warp is the least a warp can take
     if (grid > needed) grid = needed;
     k<<<grid, POOL_WARPS * 32, smem, stream>>>(sc, fp, d_out, pixelCounter, pp, reinterpret_cast<HitRecord*>(hits), hitCount, stats);

@@ -135,8 +135,8 @@ def test_fused_shadow_continuation_equals_hit_record_path(rb, pyport, load_scene
 @pytest.mark.parametrize("model,size", [("chessboard.tri", (1920, 1080)), ("dragon_vis.ply", (1280, 720)), ("single.ply", (320, 240)),
                                         ("trainColor.tri", (800, 600)), ("torus.ply", (640, 480))])
 def test_pool_overflow_guard_and_legacy_pipeline_agree(rb, pyport, load_scene, gpu, model, size, flags):
-    """rt_pool_kernel with 2-entry private stacks (full stacks - the lane walks the subtree on the spot - and the wide conversion
-    happen all the time) and round 1's lane-per-job pipeline against the default kernel: identical frames, fused and generic
+    """rt_pool_kernel with 128-entry pools (the overflow guard - lanes walking whole subtrees with a private stack - runs all
+    the time) and round 1's lane-per-job pipeline against the default 512-entry pools: identical frames, fused and generic
     configurations, and equal to the oracle."""
     import numpy as np
     s = load_scene(model)
@@ -146,7 +146,7 @@ def test_pool_overflow_guard_and_legacy_pipeline_agree(rb, pyport, load_scene, g
         pool = gpu.render(f)
         with gpu.switch("pool_small"):
             small = gpu.render(f)
-        assert np.array_equal(small, pool), f"{model} frame {k} flags={flags}: 2-entry private stacks"
+        assert np.array_equal(small, pool), f"{model} frame {k} flags={flags}: 128-entry pools"
         with gpu.switch("rt_legacy"):
             legacy = gpu.render(f)
         assert np.array_equal(legacy, pool), f"{model} frame {k} flags={flags}: job pipeline"
@@ -156,29 +156,23 @@ def test_pool_overflow_guard_and_legacy_pipeline_agree(rb, pyport, load_scene, g
 
 @pytest.mark.parametrize("model,size", [("chessboard.tri", (1920, 1080)), ("dragon_vis.ply", (801, 603)), ("torus.ply", (64, 48))])
 def test_pool_scheduling_variants_change_nothing(rb, load_scene, gpu, model, size):
-    """How rt_pool_kernel deals pixels to warps (scattered 4-pixel groups / whole tiles), when rays turn wide (after 1 step:
-    every ray spreads over the lanes at once; after 8; default) and when its passes run (thresholds) is scheduling only:
-    every combination must give the same frame, fused and generic configurations."""
+    """How rt_pool_kernel deals pixels to warps (scattered 4-pixel groups / whole tiles) and pops its pool (policies 0, 1, 2) is
+    scheduling only: every combination must give the same frame, fused and generic configurations."""
     import numpy as np
     s = load_scene(model)
     gpu.upload(s)
     cam = rb.Orbit.cameras([21])[21]
-    variants = [dict(pool_no_scatter=1), dict(pool_wide_after=1), dict(pool_wide_after=8, pool_no_scatter=1),
-                dict(pool_wide_after=100000), dict(pool_leaf_min=1, pool_sort_min=1, pool_shade_min=1, pool_refill_min=1),
-                dict(pool_leaf_min=32, pool_sort_min=32, pool_shade_min=32, pool_refill_min=32, pool_dry=1),
-                dict(pool_small=1, pool_wide_after=3), dict(pool_dry=200)]
     for flags in (1 | 4, 1 | 2 | 4):
         f = rb.make_frame(rb.MODE_RAYTRACE, size[0], size[1], cam, flags=flags)
         base = gpu.render(f)
-        for v in variants:
-            for k, val in v.items():
-                gpu.set_switch(k, val)
-            try:
-                got = gpu.render(f)
-            finally:
-                for k in v:
-                    gpu.set_switch(k, 0)
-            assert np.array_equal(got, base), f"{model} flags={flags} {v}"
+        for scatter_off in (0, 1):
+            for policy in (0, 1, 2, 3):
+                gpu.set_switch("pool_no_scatter", scatter_off); gpu.set_switch("pool_policy", policy)
+                try:
+                    got = gpu.render(f)
+                finally:
+                    gpu.set_switch("pool_no_scatter", 0); gpu.set_switch("pool_policy", 0)
+                assert np.array_equal(got, base), f"{model} flags={flags} no_scatter={scatter_off} policy={policy}"
 
 
 @pytest.mark.parametrize("model", ["chessboard.tri", "dragon_vis.ply", "trainColor.tri"])

@@ -17,8 +17,8 @@ L = rb.lib()
 g.set_switch("pool_stats", 1)
 g.render(f)
 c = list(g.counters().values())
-names = ["inner", "leaf", "shade", "refill"]
+names = ["inner", "leaf", "resolve", "refill", "guard"]
 out = {n: {"iterations": c[2 * i], "lanes": c[2 * i + 1], "lanes_per_iteration": round(c[2 * i + 1] / max(c[2 * i], 1), 2)} for i, n in enumerate(names)}
-out["rays_turned_wide"] = c[8] & 0xffffffff; out["subtrees_walked_on_the_spot"] = c[8] >> 32; out["inner_steps_of_wide_rays"] = c[10]
-out["max_iterations_of_a_warp"] = c[9]; out["warps"] = 148 * 3 * 8; out["kernel_ms"] = g.last_kernel_ms()[0]
+out["inner_pops_dropped"] = c[10]; out["cold_pops"] = c[8] >> 32; out["guard"]["iterations"] &= 0xffffffff
+out["max_iterations_of_a_warp"] = c[9]; out["guard"]["lanes"] = 0; out["warps"] = 148 * 3 * 8; out["kernel_ms"] = g.last_kernel_ms()[0]
 print(json.dumps(out))
