@@ -209,7 +209,7 @@ def cpu_reference(wl, target_seconds=15.0, rays_per_frame=None, runner=None):
     if that binary was not built."""
     from oracle import pyport
     if rays_per_frame is None:
-        rays_per_frame = 0 if wl.get("raster") else port_rays_per_frame(wl)
+        rays_per_frame = 0.0
     r = runner or RefRunner(wl)
     if r.ok:
         if r.fps0 is None:
@@ -236,19 +236,22 @@ def cpu_reference(wl, target_seconds=15.0, rays_per_frame=None, runner=None):
             "sample": f"{n} orbit frames of [{wl['desc']}] by oracle/port (C++ restatement, OpenMP over rows)"}
 
 
-def port_rays_per_frame(wl, frames=(0,)):
-    """Rays (BVH_IntersectTriangles invocations) per orbit frame, counted by the CPU restatement: mean over `frames`."""
-    import renderer_b200 as rb
-    from oracle import pyport
-    model = pyport.model_path(wl["model"])
-    scene = rb.Scene(model).UpdateBoundingVolumeHierarchy(model + ".bvh")
-    cams = rb.Orbit.cameras(range(max(frames) + 1))
-    total = 0
-    for k in frames:
-        f = rb.make_frame(wl["mode"], wl["W"], wl["H"], cams[k], flags=wl["flags"], ao_samples=wl["ao"] or 32, frame_index=k)
-        _, c = pyport.render(scene, f, counters=True)
-        total += c["rays_primary"] + c["rays_shadow"] + c["rays_reflection"] + c["rays_ao"]
-    return total / len(frames)
+def fixture_rays_per_frame(workload, frames):
+    """Rays per orbit frame (mean over `frames`) from tests/golden/rays_per_frame.json - counted once by the CPU restatement
+    (tests/golden/make_rays_per_frame.py); frames between two stored ones are interpolated. Nothing of the product is loaded."""
+    with open(os.path.join(ROOT, "tests", "golden", "rays_per_frame.json")) as f:
+        d = {int(k): float(v) for k, v in json.load(f)[workload].items()}
+    ks = sorted(d)
+
+    def at(k):
+        if k <= ks[0]:
+            return d[ks[0]]
+        if k >= ks[-1]:
+            return d[ks[-1]]
+        hi = next(i for i in ks if i >= k)
+        lo = max(i for i in ks if i <= k)
+        return d[lo] if hi == lo else d[lo] + (d[hi] - d[lo]) * (k - lo) / (hi - lo)
+    return sum(at(k) for k in frames) / len(frames)
 
 
 def run_reference_arm(args, wl):
@@ -259,7 +262,7 @@ def run_reference_arm(args, wl):
     raster = bool(wl.get("raster"))
     # rays per frame: mean over five frames spread over the orbit frames the B200 arm times (warmup .. warmup+steps-1)
     K, Wm = max(1, args.steps), args.warmup
-    rays = 0 if raster else port_rays_per_frame(wl, frames=sorted({Wm + (K - 1) * q // 4 for q in range(5)}))
+    rays = 0 if raster else fixture_rays_per_frame(args.workload, sorted({Wm + (K - 1) * q // 4 for q in range(5)}))
     # each "step" is a bounded sample: the reference renders a batch of orbit frames; K+W batches in total
     per_step = max(1.5, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
     vals = []
@@ -308,6 +311,7 @@ def run_b200_arm(args, wl):
         dist = init_nccl(local)
 
     W, H = wl["W"], wl["H"]
+    raster = bool(wl.get("raster"))
     model = pyport.model_path(wl["model"])
     scene = rb.Scene(model).UpdateBoundingVolumeHierarchy(model + ".bvh")
     gpu = rb.Renderer(local)
@@ -316,158 +320,157 @@ def run_b200_arm(args, wl):
     K, Wm = args.steps, args.warmup
     cams = rb.Orbit.cameras(range(K + Wm))
     rows_per = (H + P - 1) // P
+    assemble = {"nccl": rb.ASSEMBLE_NCCL, "push": rb.ASSEMBLE_PUSH}[os.environ.get("B200R_ASSEMBLE", "push")]
 
-    def frame_for(step, full=False):
+    def frame_for(step, sharded=False):
         return rb.make_frame(wl["mode"], W, H, cams[step], flags=wl["flags"], ao_samples=wl["ao"] or 32,
-                             frame_index=step, row_first=0 if full else rank, row_step=1 if full else P)
+                             frame_index=step, row_first=rank if sharded else 0, row_step=P if sharded else 1)
 
-    # Everything timed runs on ONE explicit stream: the L2 flush, the events, the renderer's kernels (b200r_render_device enqueues on
-    # the stream it is given; the legacy default stream, handle 0, would mean "library stream + host sync") and NCCL's waits.
+    def job_id():
+        """One NCCL unique id per pipeline, created on rank 0 and handed out over torch.distributed (plumbing)."""
+        if P == 1:
+            return None
+        uid = [rb.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        return uid[0]
+
+    # Everything timed is ordered against ONE explicit stream: the L2 flush, the events, the renderer's kernels.
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
     assert sptr != 0
-    shard = torch.zeros((rows_per, W), dtype=torch.int32, device="cuda")
-    gathered = torch.zeros((P * rows_per, W), dtype=torch.int32, device="cuda") if P > 1 else None
-    full = torch.zeros((H, W), dtype=torch.int32, device="cuda")
-    host = torch.zeros((H, W), dtype=torch.int32).pin_memory()
+    mine = torch.zeros((rows_per if P > 1 else H, W), dtype=torch.int32, device="cuda")      # this rank's rows (device-resident output)
     flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device="cuda")
-
-    def step_device(step):
-        """One frame, inputs resident, on torch's current stream. Returns my kernel launches."""
-        if P == 1:
-            gpu.render_device(frame_for(step), full.data_ptr(), sptr)
-            return gpu.last_launches()
-        gpu.render_device(frame_for(step), shard.data_ptr(), sptr)
-        n = gpu.last_launches()
-        dist.all_gather_into_tensor(gathered, shard)
-        gpu.deinterleave_device(gathered.data_ptr(), full.data_ptr(), W, H, P, sptr)
-        return n + 1
-
-    def step_e2e(step, pipelined=True):
-        """The user-facing call with HOST buffers: per-frame state in (kernel args), frame out to host memory.
-        1 GPU: b200r_render_async (the benchmark-loop call: frame i's copy-out overlaps frame i+1's kernels, two
-        page-locked host frames alternate) - every frame is complete in host memory when the timed region ends
-        (gpu.wait() before the clock stops); pipelined=False times the blocking b200r_render instead."""
-        if P == 1:
-            if pipelined:
-                gpu.render_async(frame_for(step), host_ring[step % len(host_ring)])
-            else:
-                gpu.render(frame_for(step), out=host_np)
-        else:
-            step_device(step)
-            if rank == 0:
-                host.copy_(full, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-
-    host_np = host.numpy().view(np.uint32)
-    host2 = torch.zeros((H, W), dtype=torch.int32).pin_memory()
-    host3 = torch.zeros((H, W), dtype=torch.int32).pin_memory()
-    host_ring = [host_np, host2.numpy().view(np.uint32), host3.numpy().view(np.uint32)]
 
     def barrier():
         if P > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- counters of every timed frame (untimed counting pass; counting slows the kernel)
+    # ---- counters of every timed frame (untimed counting pass; counting runs the reference's own traversal order, no pruning)
     gpu.set_counters(True)
     per_frame = []
     for s in range(Wm, Wm + K):
-        gpu.render_device(frame_for(s, full=(P == 1)), (full if P == 1 else shard).data_ptr(), None)
+        gpu.render_device(frame_for(s, sharded=P > 1), mine.data_ptr(), None)
         per_frame.append(gpu.counters())
     gpu.set_counters(False)
-    raster = bool(wl.get("raster"))
     keys = ("rays_primary", "rays_shadow", "rays_reflection", "rays_ao", "node_tests", "leaf_visits", "tri_tests",
             "tris_setup", "spans", "z_tests", "z_passes")
     tot = {k: sum(c[k] for c in per_frame) for k in keys}
     if P > 1:
         t = torch.tensor([tot[k] for k in keys], dtype=torch.int64, device="cuda")
-        mine = t.clone()
+        me = t.clone()
         dist.all_reduce(t)
         tot_all = {k: int(v) for k, v in zip(keys, t.tolist())}
-        tot_mine = {k: int(v) for k, v in zip(keys, mine.tolist())}
+        tot_mine = {k: int(v) for k, v in zip(keys, me.tolist())}
     else:
         tot_all = tot_mine = tot
     rays_total = tot_all["rays_primary"] + tot_all["rays_shadow"] + tot_all["rays_reflection"] + tot_all["rays_ao"]
     unit = "fps" if raster else "Mrays/s"
+    peak, peak_src = measured_peaks()
+    alg_bytes_mine = algorithmic_bytes(tot_mine, W, (rows_per if P > 1 else H) * K, raster)
 
-    # ---- device-timed run: W warm-up steps, then exactly K steps
+    def roofline_of(kernel_ms_avg, note):
+        achieved = (alg_bytes_mine / K) / (kernel_ms_avg / 1000.0) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.workload)
+            except Exception:
+                traffic = None
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": ("rasteriser step = clears + ras_setup + ras_depth + ras_resolve (+ the MLAA kernels)" if raster else
+                           "ray-tracing step of this rank = frame clear + rt_pool_kernel (dominant; in the C2 configuration it shades and "
+                           "casts the shadow rays itself) [+ rt_shade_kernel for AO / reflections]"),
+                "kernel_ms": kernel_ms_avg, "algorithmic_bytes_per_launch": alg_bytes_mine / K,
+                "peak_source": peak_src + " (of measured)", "how": note}
+
+    # ---- protocol 1, `serial`: one frame at a time. Per step: L2 flush (outside the events), event, this rank's kernels, event,
+    # [N > 1: assembly on every rank], event. This is the run the stand-alone kernel time comes from.
+    pipe1 = rb.Pipeline(gpu, W, H, depth=1, rank=rank, world=P, unique_id=job_id(), assemble=assemble) if P > 1 else None
     for s in range(Wm):
-        step_device(s)
+        gpu.render_device(frame_for(s, sharded=P > 1), mine.data_ptr(), sptr)
+        if pipe1:
+            pipe1.submit(frame_for(s))
+    if pipe1:
+        pipe1.drain()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(4)) for _ in range(K)]
-    launches = 0
-    t_wall0 = time.perf_counter()
+    ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(K)]
+    serial_launches = 0
     for i in range(K):
         flush.zero_()                       # evict the 126 MB L2 between timed iterations (not timed)
         ev[i][0].record()
         if P == 1:
-            launches += step_device(Wm + i)
+            gpu.render_device(frame_for(Wm + i), mine.data_ptr(), sptr)
+            serial_launches += gpu.last_launches()
             ev[i][1].record()
         else:
-            gpu.render_device(frame_for(Wm + i), shard.data_ptr(), sptr)
-            launches += gpu.last_launches() + 1
+            # the whole step through the pipeline (depth 1): render my rows, assemble on every rank
             ev[i][1].record()
-            dist.all_gather_into_tensor(gathered, shard)
-            ev[i][3].record()
-            gpu.deinterleave_device(gathered.data_ptr(), full.data_ptr(), W, H, P, sptr)
+            pipe1.fence(sptr, True)
+            pipe1.submit(frame_for(Wm + i))
+            pipe1.fence(sptr, False)
         ev[i][2].record()
     barrier()
-    wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if sampler else None
-    step_ms = [e[0].elapsed_time(e[2]) for e in ev]
-    kern_ms = [e[0].elapsed_time(e[1]) for e in ev]
-    total_ms = sum(step_ms)
-    kern_total_ms = sum(kern_ms)
+    serial_total_ms = sum(e[0].elapsed_time(e[2]) for e in ev)
+    if P == 1:
+        kern_alone_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
+    else:
+        serial_launches = pipe1.launches(reset=True)
+        # this rank's kernels alone (no assembly), same flush protocol: the stand-alone kernel time of a rank's shard
+        kev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(2)) for _ in range(K)]
+        for i in range(K):
+            flush.zero_()
+            kev[i][0].record()
+            gpu.render_device(frame_for(Wm + i, sharded=True), mine.data_ptr(), sptr)
+            kev[i][1].record()
+        barrier()
+        kern_alone_ms = sum(e[0].elapsed_time(e[1]) for e in kev) / K
     per_rank = None
     if P > 1:
-        gather_ms = sum(e[1].elapsed_time(e[3]) for e in ev)          # includes waiting for the slowest rank's kernels
-        mine = torch.tensor([total_ms, kern_total_ms, gather_ms], dtype=torch.float64, device="cuda")
-        allr = [torch.zeros_like(mine) for _ in range(P)]
-        dist.all_gather(allr, mine)
-        per_rank = {"step_ms": [float(a[0]) / K for a in allr], "render_kernels_ms": [float(a[1]) / K for a in allr],
-                    "all_gather_incl_wait_ms": [float(a[2]) / K for a in allr]}
-        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        me = torch.tensor([serial_total_ms / K, kern_alone_ms], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(me) for _ in range(P)]
+        dist.all_gather(allr, me)
+        per_rank = {"serial_step_ms": [float(a[0]) for a in allr], "render_kernels_alone_ms": [float(a[1]) for a in allr]}
+        t = torch.tensor([serial_total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    serial_ms_per_step = total_ms / K
-    serial_launches = launches
+        serial_total_ms = float(t.item())
+        barrier()
+        pipe1.close()
+    serial_ms_per_step = serial_total_ms / K
 
-    # ---- the same K steps with frames IN FLIGHT (the product's mode for independent frames, renderer_b200.dist.FramePipeline):
-    # frame i+1's kernels start while frame i's last long rays are still being walked, and (N > 1) the all-gather of frame i is
-    # on the wire while the next frames render. The L2 flush stays: one > L2 write enqueued on the frame's stream before every
-    # frame, INSIDE the timed region. One start event before the first flush, one end event after every stream has joined.
-    depth = int(os.environ.get("B200R_BENCH_DEPTH", "0")) or (0 if raster else (DEFAULT_DEPTH if P == 1 else DEFAULT_DEPTH_SHARDED))
+    # ---- protocol 2, the headline `value`: the same K steps with frames IN FLIGHT through b200r_pipeline (the product's mode for
+    # independent frames - the reference's own -b loop): frame i+1's kernels start while frame i's tail is still running, and (N > 1)
+    # frame i is assembled while the next frames render. The L2 flush stays: one > L2 write enqueued on the frame's stream before every
+    # frame, INSIDE the timed region, followed by a bulk L2 prefetch of the scene. One start event, one end event after every stream
+    # of the pipeline has joined the timing stream; max over ranks.
+    depth = int(os.environ.get("B200R_BENCH_DEPTH", "0")) or (DEFAULT_DEPTH if P == 1 else DEFAULT_DEPTH_SHARDED)
+    do_flush = os.environ.get("B200R_BENCH_FLUSH", "1") != "0"
     pipe_ms_per_step = None
-    if depth >= 1:
-        from renderer_b200.dist import FramePipeline
-        do_flush = os.environ.get("B200R_BENCH_FLUSH", "1") != "0"
-
-        def flush_on(s_):
-            with torch.cuda.stream(s_):
-                flush.zero_()
-        pipe = FramePipeline(gpu, W, H, rank=rank, world=P, depth=depth, pre_frame=flush_on if do_flush else None)
+    enqueue_ms_per_step = None
+    if not raster:
+        pipe = rb.Pipeline(gpu, W, H, depth=depth, rank=rank, world=P, unique_id=job_id(), assemble=assemble)
+        if do_flush:
+            pipe.set_l2_flush(FLUSH_BYTES, prefetch_scene=os.environ.get("B200R_BENCH_PREFETCH", "1") != "0")
         frames = [frame_for(s_) for s_ in range(Wm + K)]         # frame state prepared outside the timed region (12 floats each)
-        fake = int(os.environ.get("B200R_BENCH_FAKE_SHARD", "0"))   # developer experiment: one GPU renders rows 0, P, 2P.. only
-        if fake > 1 and P == 1:
-            for f_ in frames:
-                f_.row_first, f_.row_step = 0, fake
         for s_ in range(Wm):
             pipe.submit(frames[s_])
         pipe.drain()
         barrier()
-        pipe.launches = 0
+        pipe.launches(reset=True)
+        pipe.set_timing(True)
         sampler2 = ClockSampler(local) if rank == 0 else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_wall0 = time.perf_counter()
         e0.record(stream)
-        pipe.start_after(stream)
+        pipe.fence(sptr, True)
         for i in range(K):
             pipe.submit(frames[Wm + i])
         enqueue_ms_per_step = (time.perf_counter() - t_wall0) * 1000.0 / K     # host time to enqueue one frame (all its stages)
-        pipe.join(stream)
+        pipe.fence(sptr, False)
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - t_wall0
@@ -478,80 +481,73 @@ def run_b200_arm(args, wl):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             pipe_total_ms = float(t.item())
         pipe_ms_per_step = pipe_total_ms / K
-        launches = pipe.launches
+        launches = pipe.launches()
+        ksum, kn = pipe.kernel_ms()
+        pipe.set_timing(False)
+        kern_inflight_ms = ksum / max(kn, 1)
         if clocks2 and clocks2.get("sm_mhz"):
             clocks = clocks2
-    ms_per_step = pipe_ms_per_step if pipe_ms_per_step is not None else serial_ms_per_step
-    total_ms = ms_per_step * K
-    fps = 1000.0 / ms_per_step
-    value = fps if raster else rays_total / (total_ms / 1000.0) / 1e6
-
-    # ---- end-to-end through the public call with host buffers
-    e2e_depth = int(os.environ.get("B200R_E2E_DEPTH", "0")) or (2 if raster else (DEFAULT_DEPTH if P == 1 else DEFAULT_DEPTH_SHARDED))
-    if P == 1:
-        gpu.set_pipeline_depth(e2e_depth)
-        host_ring.extend(torch.zeros((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
-                         for _ in range(e2e_depth + 1 - len(host_ring)))
-    e2e_pipe = None
-    if P > 1 and not raster:
-        from renderer_b200.dist import FramePipeline
-        e2e_pipe = FramePipeline(gpu, W, H, rank=rank, world=P, depth=e2e_depth, to_host=(rank == 0))
-        e2e_frames = [frame_for(s_) for s_ in range(Wm + K)]
-
-    def time_e2e(pipelined):
-        if e2e_pipe is not None:
-            # N > 1: every rank keeps e2e_depth frames in flight; rank 0 also copies every assembled frame to page-locked host
-            # memory (on the comm stream, behind the all-gather + de-interleave of that frame)
-            for s_ in range(min(Wm, 3)):
-                e2e_pipe.submit(e2e_frames[s_])
-            e2e_pipe.drain()
-            barrier()
-            t0 = time.perf_counter()
-            for i in range(K):
-                e2e_pipe.submit(e2e_frames[Wm + i])
-            e2e_pipe.drain()                 # every frame of the timed region is complete in rank 0's host memory
-            barrier()
-            dt = time.perf_counter() - t0
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
+        # ---- end to end through the same public call with HOST buffers: every assembled frame is copied to page-locked host memory
+        # of rank 0 (N = 1: of the one rank) inside the timed region; no L2 flush here (the user-facing call has none)
+        pipe.set_l2_flush(0)
+        e2e_depth = int(os.environ.get("B200R_E2E_DEPTH", "0")) or depth
+        hosts = [torch.zeros((H, W), dtype=torch.int32).pin_memory() for _ in range(depth)] if rank == 0 else None
         for s_ in range(min(Wm, 3)):
-            step_e2e(s_, pipelined)
-        if P == 1:
-            gpu.wait()
+            pipe.submit(frames[s_], hosts[s_ % depth].data_ptr() if hosts else None)
+        pipe.drain()
         barrier()
         t0 = time.perf_counter()
         for i in range(K):
-            step_e2e(Wm + i, pipelined)
-        if P == 1:
-            gpu.wait()                       # every frame of the timed region is now complete in host memory
+            pipe.submit(frames[Wm + i], hosts[i % depth].data_ptr() if hosts else None)
+        pipe.drain()                     # every frame of the timed region is complete in rank 0's host memory
         barrier()
-        dt = time.perf_counter() - t0
+        e2e_s = time.perf_counter() - t0
         if P > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        return dt
+            e2e_s = float(t.item())
+        barrier()
+        pipe.close()
+        e2e_note = (f"b200r_pipeline_submit with a page-locked host frame per step: frame state in, the assembled XRGB frame out to rank 0's host "
+                    f"memory; {e2e_depth} frames in flight per rank; every frame is complete in host memory before the clock stops (b200r_pipeline_drain "
+                    "+ barrier); wall clock, max over ranks")
+        e2e_sync_s = None
+    else:
+        # rasteriser: one frame at a time on the device (value = serial); end to end through b200r_render_async / b200r_render
+        wall = serial_total_ms / 1000.0
+        launches = serial_launches
+        e2e_depth = int(os.environ.get("B200R_E2E_DEPTH", "0")) or 2
+        gpu.set_pipeline_depth(e2e_depth)
+        ring = [torch.zeros((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32) for _ in range(e2e_depth + 1)]
 
-    e2e_s = time_e2e(True)
-    e2e_sync_s = time_e2e(False) if P == 1 else e2e_s
+        def time_e2e(pipelined):
+            for s_ in range(min(Wm, 3)):
+                (gpu.render_async if pipelined else gpu.render)(frame_for(s_), ring[s_ % len(ring)])
+            gpu.wait()
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(K):
+                if pipelined:
+                    gpu.render_async(frame_for(Wm + i), ring[i % len(ring)])
+                else:
+                    gpu.render(frame_for(Wm + i), out=ring[0])
+            gpu.wait()                       # every frame of the timed region is now complete in host memory
+            barrier()
+            return time.perf_counter() - t0
+        e2e_s = time_e2e(True)
+        e2e_sync_s = time_e2e(False)
+        e2e_note = ("b200r_render_async + b200r_wait with page-locked host frames: frame state in, XRGB frame out, per step; every frame is "
+                    "complete in host memory before the clock stops; fps_blocking_call = one blocking b200r_render per step")
+    ms_per_step = pipe_ms_per_step if pipe_ms_per_step is not None else serial_ms_per_step
+    fps = 1000.0 / ms_per_step
+    value = fps if raster else rays_total / (ms_per_step * K / 1000.0) / 1e6
     e2e_value = K / e2e_s if raster else rays_total / e2e_s / 1e6
 
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        # roofline of the dominant kernel (the ray-tracing kernel of THIS rank): algorithmic bytes / its duration
-        alg_bytes = algorithmic_bytes(tot_mine, W, (rows_per if P > 1 else H) * K, raster)
-        achieved = alg_bytes / (kern_total_ms / 1000.0) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get(args.workload)
-            except Exception:
-                traffic = None
         cpu = None
         if P == 1 and not args.no_cpu_baseline:
             cpu = cpu_reference(wl, target_seconds=15.0, rays_per_frame=rays_total / K)
+        in_flight = depth if pipe_ms_per_step is not None else 1
         line = {
             "metric": unit, "value": value, "unit": unit, "fps": fps, "n_gpus": P, "steps": K, "warmup": Wm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -563,39 +559,35 @@ def run_b200_arm(args, wl):
                               if pipe_ms_per_step is not None and do_flush else
                               ("NOT flushed (B200R_BENCH_FLUSH=0: experiment, not a bench value)" if pipe_ms_per_step is not None else
                                "flushed between timed steps (144 MiB write, outside the events)")),
-                       "frames_in_flight": depth if pipe_ms_per_step is not None else 1,
-                       "host_enqueue_ms_per_step": enqueue_ms_per_step if pipe_ms_per_step is not None else None,
-                       **({"EXPERIMENT_fake_shard": fake} if pipe_ms_per_step is not None and fake > 1 else {}),
-                       "parallelism": "1 GPU" if P == 1 else f"row-cyclic sharding over {P} GPUs + 1 NCCL all-gather + de-interleave per frame",
+                       "frames_in_flight": in_flight,
+                       "host_enqueue_ms_per_step": enqueue_ms_per_step,
+                       "parallelism": "1 GPU" if P == 1 else
+                                      (f"row-cyclic sharding over {P} GPUs; rows assembled on every rank by " +
+                                       ("peer stores over NVLink + one arrival flag per frame (b200r_pipeline, B200R_ASSEMBLE_PUSH)"
+                                        if assemble == rb.ASSEMBLE_PUSH else "ONE ncclAllGather + de-interleave per frame (B200R_ASSEMBLE_NCCL)")),
                        "timing": ("exactly K frames between ONE start event (before the first flush) and ONE end event recorded after every "
-                                  "render/communication stream has joined the timing stream; max over ranks. Frames are independent "
-                                  "(the reference's -b orbit), so up to frames_in_flight of them overlap; `serial` below is the same K "
-                                  "frames one at a time") if pipe_ms_per_step is not None else
+                                  "stream of the pipeline has joined the timing stream; max over ranks. Frames are independent (the reference's "
+                                  "-b orbit), so up to frames_in_flight of them overlap per rank; `serial` is the same K frames one at a time")
+                                 if pipe_ms_per_step is not None else
                                  "CUDA events on the launching stream around every step, max over ranks"},
+            # one protocol per object: `roofline` belongs to the run `value` comes from (per-launch durations measured in that very run);
+            # `serial` is a first-class object with its own ms_per_step, kernel time and roofline.
+            "roofline": roofline_of(kern_inflight_ms, f"same run as `value`: CUDA events on each frame's own stream around this rank's kernels of that frame, "
+                                                      f"mean over the K timed frames. Up to {in_flight} frames are in flight, so a launch shares the SMs with its "
+                                                      "neighbours: kernel_ms can exceed ms_per_step by up to that factor; `serial.roofline` is the launch timed alone")
+                        if pipe_ms_per_step is not None else
+                        roofline_of(kern_alone_ms, "same run as `value`: CUDA events around this rank's kernels of every step"),
             "serial": {"ms_per_step": serial_ms_per_step, "fps": 1000.0 / serial_ms_per_step,
                        "value": (1000.0 / serial_ms_per_step) if raster else rays_total / (serial_ms_per_step * K / 1000.0) / 1e6,
-                       "gpu_launches": serial_launches,
-                       "note": "one frame at a time on one stream, L2 flushed (144 MiB write) between steps outside the per-step events; "
-                               "roofline.kernel_ms is this run's per-launch kernel time (a kernel timed alone)"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic,
-                         "kernel": ("rasteriser step = clears + ras_setup + ras_depth + ras_resolve (+ the 5 MLAA kernels)" if raster else
-                                    "ray-tracing step = rt_rootcull_kernel + rt_primary_kernel (dominant; shades and casts the shadow rays itself)"),
-                         "kernel_ms": kern_total_ms / K,
-                         "algorithmic_bytes_per_launch": alg_bytes / K, "peak_source": peak_src + " (of measured)"},
+                       "unit": unit, "gpu_launches": serial_launches, "frames_in_flight": 1,
+                       "roofline": roofline_of(kern_alone_ms, "one frame at a time, L2 flushed (144 MiB write) before every step outside the events; CUDA "
+                                                              "events around this rank's kernels of every step: a launch timed alone"),
+                       "note": "one frame at a time on one stream; kernel_ms <= ms_per_step holds here by construction"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": unit, "fps": K / e2e_s,
                     "h2d_bytes_per_step": C.sizeof(rb.Frame), "d2h_bytes_per_step": W * H * 4,
-                    "fps_blocking_call": K / e2e_sync_s,
-                    "frames_in_flight": e2e_depth,
-                    "note": ("b200r_render_async + b200r_wait with page-locked host frames: frame state in, XRGB frame out, per step; "
-                             f"up to {e2e_depth + 1} frames in flight (one copying out while the next {e2e_depth} render on their own streams, "
-                             "the head of one filling the SMs the tail of another leaves idle); every frame is complete in host memory "
-                             "before the clock stops; fps_blocking_call = one blocking b200r_render per step")
-                            if P == 1 else
-                            (f"renderer_b200.dist.FramePipeline: every rank renders its rows of up to {e2e_depth} frames in flight; per frame ONE "
-                             "NCCL all-gather + de-interleave on a communication stream, then rank 0 copies the assembled frame to "
-                             "page-locked host memory; every frame is complete in rank 0's host memory before the clock stops")},
+                    "frames_in_flight": e2e_depth, "note": e2e_note,
+                    **({"fps_blocking_call": K / e2e_sync_s} if e2e_sync_s else {})},
             "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall,
         }
         if per_rank:

@@ -184,6 +184,49 @@ int  b200r_mlaa_device(b200r_ctx* ctx, void* dev_xrgb, uint32_t width, uint32_t 
 int  b200r_deinterleave_device(b200r_ctx* ctx, const void* dev_gathered, void* dev_frame,
                                uint32_t width, uint32_t height, uint32_t n_shards, void* cuda_stream);
 
+/* ---------------------------------------------------------------- (1b) frames in flight / several GPUs
+ * One b200r_pipeline per rank - one process (or one thread) per GPU, each with its own b200r_ctx and the same scene uploaded.
+ * Replaces the body of main()'s benchmark loop (reference src/renderer.cc:491-606) when frames do not depend on each other:
+ * submit() returns as soon as the frame is ENQUEUED; up to `depth` frames are in flight per rank (slot = submission index % depth).
+ * With world > 1 rank r renders rows r, r+world, ... of every frame and the rows are assembled into a
+ * scan-order frame on EVERY rank, either by one ncclAllGather + a de-interleave kernel (B200R_ASSEMBLE_NCCL) or by stores
+ * through NVLink peer mappings with one arrival flag per frame (B200R_ASSEMBLE_PUSH); B200R_F_MLAA is applied to the assembled
+ * frame. Every rank must submit the same frames in the same order. Ray-tracing modes only (b200r_render_device_slot).
+ * NCCL is loaded at run time and only when world > 1. */
+#define B200R_ASSEMBLE_NCCL 0
+#define B200R_ASSEMBLE_PUSH 1
+typedef struct b200r_pipeline b200r_pipeline;
+/* 128 bytes identifying the job: created on rank 0 (ncclGetUniqueId) and handed to every rank by the launcher. */
+int  b200r_dist_unique_id(void* out128);
+int  b200r_pipeline_create(b200r_ctx* ctx, uint32_t width, uint32_t height, uint32_t depth, uint32_t rank, uint32_t world,
+                           const void* nccl_unique_id /* NULL iff world == 1 */, uint32_t assemble, b200r_pipeline** out);
+/* host_xrgb: page-locked host memory that receives the ASSEMBLED frame (complete after b200r_pipeline_drain, or once `depth`
+ * further frames were submitted and drained past it), or NULL to leave the frame on the device (b200r_pipeline_slot_frame). */
+int  b200r_pipeline_submit(b200r_pipeline* pipe, const b200r_frame* f, uint32_t* host_xrgb);
+int  b200r_pipeline_drain(b200r_pipeline* pipe);                       /* host waits for everything submitted on THIS rank */
+int  b200r_pipeline_slot_frame(b200r_pipeline* pipe, uint32_t slot, void** dev_xrgb);
+/* Order the pipeline against a caller's stream: pipeline_waits != 0 - nothing submitted from now on starts before the stream's
+ * current tail; == 0 - the stream waits for everything submitted so far (device side; the host does not block). */
+int  b200r_pipeline_fence(b200r_pipeline* pipe, void* cuda_stream, int pipeline_waits);
+/* Measurement aids (bench.py): write `bytes` (> L2) before every frame on the frame's stream, then prefetch up to four device
+ * buffers (the scene) back into L2. 0 bytes switches it off. */
+int  b200r_pipeline_set_l2_flush(b200r_pipeline* pipe, uint64_t bytes);
+int  b200r_pipeline_set_prefetch(b200r_pipeline* pipe, uint32_t index, const void* dev_ptr, uint64_t bytes);
+int  b200r_pipeline_launches(b200r_pipeline* pipe, uint32_t* n_kernel_launches, int reset);
+/* Timing on: CUDA events around this rank's render kernels of every submitted frame (on the frame's own stream);
+ * b200r_pipeline_kernel_ms waits for them and returns the sum of the durations and the number of frames since the last call. */
+int  b200r_pipeline_set_timing(b200r_pipeline* pipe, int enabled);
+int  b200r_pipeline_kernel_ms(b200r_pipeline* pipe, double* sum_ms, uint32_t* n_frames);
+const char* b200r_pipeline_last_error(const b200r_pipeline* pipe);
+/* All ranks must have drained (and agreed on it, e.g. a barrier) before any rank destroys its pipeline. */
+void b200r_pipeline_destroy(b200r_pipeline* pipe);
+/* Page-locked host memory for frames (b200r_pipeline_submit / b200r_render_async write into it by DMA). */
+int  b200r_host_alloc(uint64_t bytes, void** out);
+void b200r_host_free(void* p);
+/* Device addresses / sizes of the uploaded scene's traversal buffers (for b200r_pipeline_set_prefetch): index 0 nodes, 1 leaf
+ * triangle records, 2 shading records. Returns B200R_EINVAL past the last one. */
+int  b200r_scene_buffer(b200r_ctx* ctx, uint32_t index, const void** dev_ptr, uint64_t* bytes);
+
 /* Replaces: CreateBVH + CreateCFBVH (src/BVH.cc:96-371 scalar path, src/Raytracer.cc:651-718) ON THE DEVICE: the SAH
  * build as level-synchronous kernels (csrc/bvh_steps.h, csrc/cuda/bvh_build.cu) producing the same tree bit for bit - the
  * nodes/tri_idx written here are byte-identical to the reference's .bvh cache content. nodes_out needs room for

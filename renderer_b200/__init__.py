@@ -368,6 +368,85 @@ class Renderer:
         return self._mode(MODE_RAYTRACE_AA if antiAlias else MODE_RAYTRACE, camera, width, height, **kw)
 
 
+ASSEMBLE_NCCL, ASSEMBLE_PUSH = 0, 1
+
+
+def dist_unique_id():
+    """b200r_dist_unique_id: 128 bytes naming a multi-GPU job; create on rank 0 and hand to every rank."""
+    buf = C.create_string_buffer(128)
+    _check(lib().b200r_dist_unique_id(buf))
+    return buf.raw
+
+
+class Pipeline:
+    """b200r_pipeline: frames in flight on one rank of `world` (include/b200render.h (1b)). Rank r renders rows r, r+world, ...;
+    the rows are assembled into a scan-order frame on every rank by one NCCL all-gather (ASSEMBLE_NCCL) or by peer stores over
+    NVLink (ASSEMBLE_PUSH)."""
+
+    def __init__(self, renderer, width, height, depth=2, rank=0, world=1, unique_id=None, assemble=ASSEMBLE_PUSH):
+        self._r = renderer
+        self._p = C.c_void_p()
+        self.depth, self.rank, self.world, self.width, self.height = depth, rank, world, width, height
+        uid = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        _check(lib().b200r_pipeline_create(renderer._ctx, width, height, depth, rank, world, uid, assemble, C.byref(self._p)))
+        self._keep = []
+        self.submitted = 0
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RendererError((lib().b200r_pipeline_last_error(self._p) or b"").decode() or f"error {rc}")
+
+    def submit(self, frame, host=None):
+        """Enqueue a frame; returns its slot. `host`: page-locked numpy array (height x width uint32) or an integer address."""
+        ptr = None
+        if host is not None:
+            ptr = host if isinstance(host, int) else host.ctypes.data
+            self._keep = (self._keep + [host])[-(self.depth + 1):]
+        self._chk(lib().b200r_pipeline_submit(self._p, C.byref(frame), ptr))
+        self.submitted += 1
+        return (self.submitted - 1) % self.depth
+
+    def drain(self):
+        self._chk(lib().b200r_pipeline_drain(self._p))
+
+    def slot_frame(self, slot):
+        """Device address of the assembled frame of `slot` (valid after drain())."""
+        ptr = C.c_void_p()
+        self._chk(lib().b200r_pipeline_slot_frame(self._p, slot, C.byref(ptr)))
+        return ptr.value
+
+    def fence(self, stream, pipeline_waits):
+        self._chk(lib().b200r_pipeline_fence(self._p, C.c_void_p(stream), 1 if pipeline_waits else 0))
+
+    def set_l2_flush(self, nbytes, prefetch_scene=True):
+        """Measurement aid: evict the L2 (a write of `nbytes`) before every frame, then prefetch the scene back."""
+        self._chk(lib().b200r_pipeline_set_l2_flush(self._p, int(nbytes)))
+        for k in range(3):
+            ptr, n = C.c_void_p(), C.c_uint64()
+            if nbytes and prefetch_scene:
+                _check(lib().b200r_scene_buffer(self._r._ctx, k, C.byref(ptr), C.byref(n)), self._r._ctx)
+            self._chk(lib().b200r_pipeline_set_prefetch(self._p, k, ptr, n.value))
+
+    def launches(self, reset=False):
+        n = C.c_uint32()
+        self._chk(lib().b200r_pipeline_launches(self._p, C.byref(n), 1 if reset else 0))
+        return n.value
+
+    def set_timing(self, enabled):
+        self._chk(lib().b200r_pipeline_set_timing(self._p, 1 if enabled else 0))
+
+    def kernel_ms(self):
+        """(sum of this rank's render-kernel durations in ms, frames) since the last call; waits for the frames."""
+        s, n = C.c_double(), C.c_uint32()
+        self._chk(lib().b200r_pipeline_kernel_ms(self._p, C.byref(s), C.byref(n)))
+        return s.value, n.value
+
+    def close(self):
+        if self._p:
+            lib().b200r_pipeline_destroy(self._p)
+            self._p = C.c_void_p()
+
+
 def default_light_pos(index=0):
     p = (C.c_float * 3)()
     lib().b200r_default_light_pos(index, p)

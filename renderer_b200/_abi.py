@@ -84,6 +84,23 @@ SYMBOLS = {
     "b200r_set_tile_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "b200r_get_tile_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, P(C.c_uint32)]),
     "b200r_set_switch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "b200r_dist_unique_id": (C.c_int, [C.c_void_p]),
+    "b200r_pipeline_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32,
+                                        P(C.c_void_p)]),
+    "b200r_pipeline_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200r_pipeline_drain": (C.c_int, [C.c_void_p]),
+    "b200r_pipeline_slot_frame": (C.c_int, [C.c_void_p, C.c_uint32, P(C.c_void_p)]),
+    "b200r_pipeline_fence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "b200r_pipeline_set_l2_flush": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "b200r_pipeline_set_prefetch": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]),
+    "b200r_pipeline_launches": (C.c_int, [C.c_void_p, P(C.c_uint32), C.c_int]),
+    "b200r_pipeline_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200r_pipeline_kernel_ms": (C.c_int, [C.c_void_p, P(C.c_double), P(C.c_uint32)]),
+    "b200r_pipeline_last_error": (C.c_char_p, [C.c_void_p]),
+    "b200r_pipeline_destroy": (None, [C.c_void_p]),
+    "b200r_host_alloc": (C.c_int, [C.c_uint64, P(C.c_void_p)]),
+    "b200r_host_free": (None, [C.c_void_p]),
+    "b200r_scene_buffer": (C.c_int, [C.c_void_p, C.c_uint32, P(C.c_void_p), P(C.c_uint64)]),
     "b200r_set_counters": (C.c_int, [C.c_void_p, C.c_int]),
     "b200r_get_counters": (C.c_int, [C.c_void_p, P(Counters)]),
     "b200r_last_kernel_ms": (C.c_int, [C.c_void_p, P(C.c_float), P(C.c_float)]),

@@ -69,7 +69,7 @@ def build(force=False, verbose=False):
         _run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lpthread"], os.path.join(OBJ, "link.log"))
     main = os.path.join(CSRC, "host", "main.cpp")
     if os.path.exists(main) and (force or _newer(CLI, [main, LIB] + headers)):
-        _run(["g++"] + CXX_FLAGS + ["-o", CLI, main, "-L" + PKG, "-lb200render", "-Wl,-rpath,$ORIGIN"],
+        _run(["g++"] + CXX_FLAGS + ["-pthread", "-o", CLI, main, "-L" + PKG, "-lb200render", "-Wl,-rpath,$ORIGIN"],
              os.path.join(OBJ, "cli.log"))
     return LIB
 

@@ -25,6 +25,12 @@ uint32_t count_unbounded_triangles(const b200r_vertex* verts, uint32_t n_verts, 
 
 using namespace b200r;
 
+struct b200r_ctx;
+namespace b200r {
+int ctx_device(const b200r_ctx* ctx);
+int ctx_sms(const b200r_ctx* ctx);
+}
+
 struct b200r_ctx {
     int device = -1;
     int numSMs = 0;
@@ -37,6 +43,7 @@ struct b200r_ctx {
     float* d_shadowmap[B200R_MAX_LIGHTS] = {nullptr, nullptr};
     DeviceScene sc{};
     bool have_scene = false, have_bvh = false;
+    size_t nodesBytes = 0, leafBytes = 0, shadeBytes = 0;
 
     // frame resources
     uint32_t* d_frame = nullptr; size_t frame_words = 0;
@@ -76,6 +83,9 @@ struct b200r_ctx {
     float last_total_ms = 0.f, last_dominant_ms = 0.f;
     uint32_t last_launches = 0;
 };
+
+int b200r::ctx_device(const b200r_ctx* ctx) { return ctx->device; }
+int b200r::ctx_sms(const b200r_ctx* ctx) { return ctx->numSMs; }
 
 namespace {
 
@@ -577,6 +587,7 @@ int b200r_upload_scene(b200r_ctx* ctx, const b200r_vertex* verts, uint32_t n_ver
     CU(upload(&ctx->d_rverts, hv, ctx->stream));
     CU(upload(&ctx->d_rtris, ht, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));   // host staging vectors go out of scope
+    ctx->nodesBytes = hn.size() * sizeof(float4); ctx->leafBytes = hl.size() * sizeof(float4); ctx->shadeBytes = hs.size() * sizeof(float4);
     ctx->sc.wnodes = ctx->d_nodes; ctx->sc.leaftris = ctx->d_leaftris; ctx->sc.shade = ctx->d_shade;
     ctx->sc.rverts = ctx->d_rverts; ctx->sc.rtris = ctx->d_rtris;
     ctx->sc.n_nodes = n_nodes; ctx->sc.n_list = n_tri_idx; ctx->sc.n_tris = n_tris; ctx->sc.n_verts = n_verts;
@@ -855,6 +866,28 @@ int b200r_get_tile_profile(b200r_ctx* ctx, uint64_t* start_end_ns, uint32_t max_
     const uint32_t n = ctx->lastTiles < max_tiles ? ctx->lastTiles : max_tiles;
     CU(cudaMemcpy(start_end_ns, ctx->d_tileProf, (size_t)n * 16, cudaMemcpyDeviceToHost));
     return B200R_OK;
+}
+
+int b200r_host_alloc(uint64_t bytes, void** out)
+{
+    if (!out || !bytes) return fail(nullptr, B200R_EINVAL, "b200r_host_alloc: bad argument");
+    cudaError_t e = cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) return fail(nullptr, B200R_ENOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    return B200R_OK;
+}
+
+void b200r_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int b200r_scene_buffer(b200r_ctx* ctx, uint32_t index, const void** dev_ptr, uint64_t* bytes)
+{
+    if (!ctx || !dev_ptr || !bytes) return fail(ctx, B200R_EINVAL, "NULL argument");
+    if (!ctx->have_scene) return fail(ctx, B200R_ESTATE, "no scene uploaded");
+    switch (index) {
+    case 0: *dev_ptr = ctx->d_nodes; *bytes = (uint64_t)ctx->nodesBytes; return B200R_OK;
+    case 1: *dev_ptr = ctx->d_leaftris; *bytes = (uint64_t)ctx->leafBytes; return B200R_OK;
+    case 2: *dev_ptr = ctx->d_shade; *bytes = (uint64_t)ctx->shadeBytes; return B200R_OK;
+    default: return fail(ctx, B200R_EINVAL, "no such scene buffer");
+    }
 }
 
 int b200r_set_counters(b200r_ctx* ctx, int enabled)

@@ -64,119 +64,22 @@ def test_two_rank_gloo_frame_assembly(pyport):
     assert all(n > 0 for _, _, n in res)
 
 
-def test_frame_pipeline_orders_its_stages(monkeypatch):
-    """renderer_b200.dist.FramePipeline on a recording stand-in for torch.cuda / NCCL (no GPU): per frame the render stream waits
-    for its slot's previous frame, the all-gather follows the render through an event on the communication stream, the
-    de-interleave follows the all-gather, the copy-out follows the assembly on its own stream, and the slot is only released
-    after the copy - for every slot of a 3-deep pipeline on rank 0 of 2."""
-    import sys
-    import types
-    log = []
+def test_pipeline_api_refuses_bad_arguments_without_a_device(rb):
+    """The C-ABI frame pipeline (b200r_pipeline_*, csrc/cuda/dist.cu) checks its arguments before touching a device; without a
+    context there is nothing it could run on - it must fail, not fall back."""
+    import ctypes as C
+    L = rb.lib()
+    out = C.c_void_p()
+    assert L.b200r_pipeline_create(None, 64, 48, 2, 0, 1, None, rb.ASSEMBLE_PUSH, C.byref(out)) != 0
+    assert not out.value
+    assert L.b200r_pipeline_submit(None, None, None) != 0
+    assert L.b200r_pipeline_drain(None) != 0
+    L.b200r_pipeline_destroy(None)                     # no-op
 
-    class Event:
-        n = 0
 
-        def __init__(self, **kw):
-            Event.n += 1
-            self.id = Event.n
-
-        def record(self, stream):
-            log.append(("record", self.id, stream.name))
-
-    class Stream:
-        n = 0
-
-        def __init__(self, priority=0):
-            Stream.n += 1
-            self.name = f"s{Stream.n}"
-            self.cuda_stream = 1000 + Stream.n
-
-        def wait_event(self, ev):
-            log.append(("wait_event", ev.id, self.name))
-
-        def wait_stream(self, other):
-            log.append(("wait_stream", other.name, self.name))
-
-        def synchronize(self):
-            log.append(("sync", self.name))
-
-    class Tensor:
-        def __init__(self, name):
-            self.name = name
-
-        def data_ptr(self):
-            return hash(self.name) & 0xffff
-
-        def pin_memory(self):
-            return self
-
-        def copy_(self, src, non_blocking=False):
-            log.append(("copy", src.name, self.name, current[-1].name))
-
-    current = [types.SimpleNamespace(name="default")]
-    counter = {"t": 0}
-
-    class StreamCtx:
-        def __init__(self, s):
-            self.s = s
-
-        def __enter__(self):
-            current.append(self.s)
-
-        def __exit__(self, *a):
-            current.pop()
-
-    def zeros(shape, **kw):
-        counter["t"] += 1
-        return Tensor(f"t{counter['t']}_{shape[0]}x{shape[1]}")
-
-    cuda = types.SimpleNamespace(Stream=Stream, Event=Event, stream=StreamCtx, current_device=lambda: 0, synchronize=lambda: None)
-    torch = types.ModuleType("torch")
-    torch.cuda, torch.int32, torch.zeros, torch.device = cuda, "int32", zeros, (lambda *a: "cuda:0")
-    tdist = types.ModuleType("torch.distributed")
-    tdist.all_gather_into_tensor = lambda out, inp, group=None: log.append(("all_gather", inp.name, out.name, current[-1].name))
-    torch.distributed = tdist
-    monkeypatch.setitem(sys.modules, "torch", torch)
-    monkeypatch.setitem(sys.modules, "torch.distributed", tdist)
-
-    class Gpu:
-        def render_device_slot(self, frame, ptr, stream, slot):
-            log.append(("render", frame, stream, slot))
-
-        def deinterleave_device(self, g, f, W, H, P, stream):
-            log.append(("deinterleave", stream))
-
-        def last_launches(self):
-            return 2
-
-    from renderer_b200.dist import FramePipeline
-    D = 3
-    pipe = FramePipeline(Gpu(), 64, 48, rank=0, world=2, depth=D, to_host=True)
-    comm, copy = pipe.comm, pipe.copy
-    for i in range(2 * D + 1):
-        del log[:]
-        d = pipe.submit(f"frame{i}")
-        assert d == i % D
-        rs = pipe.render_streams[d]
-        kinds = [e[0] for e in log]
-        # the order of everything enqueued for this frame
-        assert kinds == (["wait_event"] if i >= D else []) + ["render", "record", "wait_event", "all_gather", "deinterleave",
-                                                               "record", "wait_event", "copy", "record"]
-        it = iter(log)
-        if i >= D:
-            assert next(it) == ("wait_event", pipe.free[d].id, rs.name)              # slot d's previous frame has been copied out
-        assert next(it) == ("render", f"frame{i}", rs.cuda_stream, d)
-        assert next(it) == ("record", pipe.rendered[d].id, rs.name)
-        assert next(it) == ("wait_event", pipe.rendered[d].id, comm.name)
-        assert next(it) == ("all_gather", pipe.shard[d].name, pipe.gathered[d].name, comm.name)
-        assert next(it) == ("deinterleave", comm.cuda_stream)
-        assert next(it) == ("record", pipe.assembled[d].id, comm.name)
-        assert next(it) == ("wait_event", pipe.assembled[d].id, copy.name)
-        assert next(it) == ("copy", pipe.full[d].name, pipe.host[d].name, copy.name)
-        assert next(it) == ("record", pipe.free[d].id, copy.name)
-    assert pipe.launches == (2 + 1) * (2 * D + 1)
-    # one GPU, frames staying on the device: no communication stream work at all, the slot is released by the render stream
-    pipe1 = FramePipeline(Gpu(), 64, 48, depth=2)
-    del log[:]
-    pipe1.submit("f0")
-    assert [e[0] for e in log] == ["render", "record", "record"] and log[-1] == ("record", pipe1.free[0].id, pipe1.render_streams[0].name)
+def test_row_ownership_matches_the_device_convention():
+    """b200r_pipeline stamps row_first = rank, row_step = world into every frame (dist.cu); the host mirror deals the same rows."""
+    from renderer_b200 import dist
+    for H, P in ((1080, 8), (2160, 8), (603, 4), (7, 3)):
+        for r in range(P):
+            assert dist.shard_rows(H, P, r) == [r + k * P for k in range((H - r + P - 1) // P)]
