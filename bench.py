@@ -451,7 +451,7 @@ def run_b200_arm(args, wl):
     do_flush = os.environ.get("B200R_BENCH_FLUSH", "1") != "0"
     pipe_ms_per_step = None
     enqueue_ms_per_step = None
-    if not raster:
+    if True:
         pipe = rb.Pipeline(gpu, W, H, depth=depth, rank=rank, world=P, unique_id=job_id(), assemble=assemble)
         if do_flush:
             pipe.set_l2_flush(FLUSH_BYTES, prefetch_scene=os.environ.get("B200R_BENCH_PREFETCH", "1") != "0")
@@ -511,33 +511,6 @@ def run_b200_arm(args, wl):
         e2e_note = (f"b200r_pipeline_submit with a page-locked host frame per step: frame state in, the assembled XRGB frame out to rank 0's host "
                     f"memory; {e2e_depth} frames in flight per rank; every frame is complete in host memory before the clock stops (b200r_pipeline_drain "
                     "+ barrier); wall clock, max over ranks")
-        e2e_sync_s = None
-    else:
-        # rasteriser: one frame at a time on the device (value = serial); end to end through b200r_render_async / b200r_render
-        wall = serial_total_ms / 1000.0
-        launches = serial_launches
-        e2e_depth = int(os.environ.get("B200R_E2E_DEPTH", "0")) or 2
-        gpu.set_pipeline_depth(e2e_depth)
-        ring = [torch.zeros((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32) for _ in range(e2e_depth + 1)]
-
-        def time_e2e(pipelined):
-            for s_ in range(min(Wm, 3)):
-                (gpu.render_async if pipelined else gpu.render)(frame_for(s_), ring[s_ % len(ring)])
-            gpu.wait()
-            barrier()
-            t0 = time.perf_counter()
-            for i in range(K):
-                if pipelined:
-                    gpu.render_async(frame_for(Wm + i), ring[i % len(ring)])
-                else:
-                    gpu.render(frame_for(Wm + i), out=ring[0])
-            gpu.wait()                       # every frame of the timed region is now complete in host memory
-            barrier()
-            return time.perf_counter() - t0
-        e2e_s = time_e2e(True)
-        e2e_sync_s = time_e2e(False)
-        e2e_note = ("b200r_render_async + b200r_wait with page-locked host frames: frame state in, XRGB frame out, per step; every frame is "
-                    "complete in host memory before the clock stops; fps_blocking_call = one blocking b200r_render per step")
     ms_per_step = pipe_ms_per_step if pipe_ms_per_step is not None else serial_ms_per_step
     fps = 1000.0 / ms_per_step
     value = fps if raster else rays_total / (ms_per_step * K / 1000.0) / 1e6
@@ -587,7 +560,7 @@ def run_b200_arm(args, wl):
             "e2e": {"value": e2e_value, "unit": unit, "fps": K / e2e_s,
                     "h2d_bytes_per_step": C.sizeof(rb.Frame), "d2h_bytes_per_step": W * H * 4,
                     "frames_in_flight": e2e_depth, "note": e2e_note,
-                    **({"fps_blocking_call": K / e2e_sync_s} if e2e_sync_s else {})},
+                    },
             "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall,
         }
         if per_rank:

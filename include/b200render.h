@@ -172,8 +172,9 @@ int  b200r_render_device(b200r_ctx* ctx, const b200r_frame* f, void* dev_xrgb, v
  * its rows of frame i+1 while the all-gather of frame i is on the wire): `scratch_slot` (0 .. B200R_MAX_FRAMES_IN_FLIGHT-1)
  * selects the set of per-frame scratch buffers (job queue, merge words, hit records). Two frames may be in flight at the
  * same time iff they use different slots; frames of the same slot must be ordered by the caller (same stream, or events).
- * `cuda_stream` must not be NULL; nothing is synchronised. Ray-tracing modes only (the rasteriser reads a span count
- * back per frame and has one scratch set): other modes return B200R_EINVAL. */
+ * `cuda_stream` must not be NULL; nothing is synchronised. Every mode but 3 (the wireframe pass sizes its fragment buffer on the
+ * host). The rasteriser's span buffer is sized up front and checked behind the frame: should a frame ever overflow it, the NEXT
+ * call on this context returns B200R_ENOMEM (the buffer has been enlarged by then; submit the frames again). */
 int  b200r_render_device_slot(b200r_ctx* ctx, const b200r_frame* f, void* dev_xrgb, void* cuda_stream, uint32_t scratch_slot);
 
 /* Replaces: MLAA(fbi, NULL, resX, resY) (src/MLAA.h:4) applied in place on a full device frame. */
@@ -191,7 +192,7 @@ int  b200r_deinterleave_device(b200r_ctx* ctx, const void* dev_gathered, void* d
  * With world > 1 rank r renders rows r, r+world, ... of every frame and the rows are assembled into a
  * scan-order frame on EVERY rank, either by one ncclAllGather + a de-interleave kernel (B200R_ASSEMBLE_NCCL) or by stores
  * through NVLink peer mappings with one arrival flag per frame (B200R_ASSEMBLE_PUSH); B200R_F_MLAA is applied to the assembled
- * frame. Every rank must submit the same frames in the same order. Ray-tracing modes only (b200r_render_device_slot).
+ * frame. Every rank must submit the same frames in the same order. Every mode but 3 (b200r_render_device_slot).
  * NCCL is loaded at run time and only when world > 1. */
 #define B200R_ASSEMBLE_NCCL 0
 #define B200R_ASSEMBLE_PUSH 1
@@ -261,7 +262,7 @@ int  b200r_get_tile_profile(b200r_ctx* ctx, uint64_t* start_end_ns, uint32_t max
 
 /* Developer switches: select cross-check variants of the kernels (parity tests, A/B measurements); none changes a result.
  * Names: monolithic_rt, no_prune, no_fuse, rt_legacy, no_root_rect, pool_small, split_depth, raster_inline_shade, mlaa_scan,
- * mlaa_fullscan, mlaa_nobatch, no_frame_overlap, bvh_serial_split, pool_stats, pool_policy, pool_no_scatter, pool_occ4,
+ * mlaa_fullscan, mlaa_nobatch, mlaa_no_tma, no_frame_overlap, bvh_serial_split, pool_stats, pool_policy, pool_no_scatter, pool_occ4, pool_tiles_per_warp,
  * pool_leaf_min, pool_sort_min, pool_shade_min, pool_refill_min, pool_low_water, pool_dry (csrc/cuda/rt_kernels.cuh `Switches` documents each).
  * Defaults come from the environment variables B200R_<NAME IN CAPITALS>, read once by b200r_init. Waits for frames in flight. */
 int  b200r_set_switch(b200r_ctx* ctx, const char* name, int value);

@@ -55,6 +55,7 @@ struct b200r_ctx {
         uint32_t* user = nullptr; size_t user_words = 0;       // where the frame finally goes
         cudaEvent_t rendered = nullptr, copied = nullptr;
         bool inflight = false, staged = false;
+        b200r_frame frame{}; int set = 0;                       // what was submitted (a rasterised frame that overflowed its span buffer is redone)
     } slot[B200R_MAX_FRAMES_IN_FLIGHT + 1];
     // frames in flight of b200r_render_async: `depth` rendering (overlapped, see rstream) + one being copied out
     unsigned depth = 2;
@@ -70,15 +71,23 @@ struct b200r_ctx {
     unsigned* d_tileCounter = nullptr;
     DeviceCounters* d_ctr = nullptr;
     Switches sw{};                                              // developer switches (b200r_set_switch / environment at b200r_init)
-    RasterBuffers rb{};
+    // rasteriser / MLAA scratch, one set per scratch slot (frames in flight); set 0 serves the blocking calls
+    struct RasterSet {
+        RasterBuffers rb{};
+        size_t zkey_pixels = 0, attr_pixels = 0;
+        float4* d_attrs = nullptr;
+        unsigned* h_spanCount = nullptr;          // pinned: the frame's span count lands here behind the frame, without a sync
+        cudaEvent_t counted = nullptr;            // recorded behind that copy
+        bool pending = false;                     // a frame whose span count has not been looked at yet
+        uint32_t* d_mlaaScratch = nullptr; size_t mlaaWords = 0;
+        void* d_mlaaLines = nullptr; size_t mlaaLinesBytes = 0;
+    } rs[B200R_MAX_FRAMES_IN_FLIGHT];
+    unsigned spanCapacityWanted = 0;              // grows when a frame overflowed
+    bool spanOverflowSticky = false;              // an un-retried frame overflowed its span buffer (device / slot calls)
     WireBuffers wb{};
-    size_t zkey_pixels = 0;
-    float4* d_attrs = nullptr; size_t attr_pixels = 0;
-    unsigned* h_spanCount = nullptr;          // pinned
+    unsigned* h_spanCount = nullptr;          // pinned (mode 3: fragment count)
     unsigned long long* d_tileProf = nullptr; size_t tileProfTiles = 0; bool tileProfile = false; uint32_t lastTiles = 0;
     unsigned* d_shadowKeys = nullptr;
-    uint32_t* d_mlaaScratch = nullptr; size_t mlaaWords = 0;
-    void* d_mlaaLines = nullptr; size_t mlaaLinesBytes = 0;
     bool counting = false;
     float last_total_ms = 0.f, last_dominant_ms = 0.f;
     uint32_t last_launches = 0;
@@ -156,34 +165,51 @@ int ensure_frame(b200r_ctx* ctx, size_t words)
     return B200R_OK;
 }
 
-int mlaa_on(b200r_ctx* ctx, uint32_t* d_frame, uint32_t width, uint32_t height, cudaStream_t s)
+int mlaa_on(b200r_ctx* ctx, uint32_t* d_frame, uint32_t width, uint32_t height, cudaStream_t s, int scratchSet = 0)
 {
+    b200r_ctx::RasterSet& R = ctx->rs[scratchSet];
     if ((width % 4) || (height % 8))
         return fail(ctx, B200R_EINVAL, "MLAA needs width % 4 == 0 and height % 8 == 0 (the reference's SSE code assumes it, MLAA.cc:396,453)");
     if (reinterpret_cast<uintptr_t>(d_frame) & 15u)
         return fail(ctx, B200R_EINVAL, "MLAA needs a 16-byte aligned frame (so does the reference's SSE code, MLAA.cc:453-457)");
     const size_t words = (size_t)width * height;
-    if (ctx->mlaaWords < words) {
-        if (ctx->d_mlaaScratch) cudaFree(ctx->d_mlaaScratch);
-        ctx->d_mlaaScratch = nullptr; ctx->mlaaWords = 0;
-        CU(cudaMalloc((void**)&ctx->d_mlaaScratch, words * 4));
-        ctx->mlaaWords = words;
+    if (R.mlaaWords < words) {
+        if (R.d_mlaaScratch) cudaFree(R.d_mlaaScratch);
+        R.d_mlaaScratch = nullptr; R.mlaaWords = 0;
+        CU(cudaMalloc((void**)&R.d_mlaaScratch, words * 4));
+        R.mlaaWords = words;
     }
     int launches = 0;
     void* lines = nullptr;
     if (!ctx->sw.mlaa_scan) {           // default: two-stage blending (all separation lines first, then the ordered blends)
         const size_t need = mlaa_lines_bytes((int)width, (int)height);
-        if (ctx->mlaaLinesBytes < need) {
-            if (ctx->d_mlaaLines) cudaFree(ctx->d_mlaaLines);
-            ctx->d_mlaaLines = nullptr; ctx->mlaaLinesBytes = 0;
-            CU(cudaMalloc(&ctx->d_mlaaLines, need));
-            ctx->mlaaLinesBytes = need;
+        if (R.mlaaLinesBytes < need) {
+            if (R.d_mlaaLines) cudaFree(R.d_mlaaLines);
+            R.d_mlaaLines = nullptr; R.mlaaLinesBytes = 0;
+            CU(cudaMalloc(&R.d_mlaaLines, need));
+            R.mlaaLinesBytes = need;
         }
-        lines = ctx->d_mlaaLines;
+        lines = R.d_mlaaLines;
     }
-    CU(launch_mlaa(d_frame, ctx->d_mlaaScratch, (int)width, (int)height, ctx->numSMs, s, launches, lines, ctx->sw));
+    CU(launch_mlaa(d_frame, R.d_mlaaScratch, (int)width, (int)height, ctx->numSMs, s, launches, lines, ctx->sw));
     ctx->last_launches += (uint32_t)launches;
     return B200R_OK;
+}
+
+// Look at the span count of the last rasterised frame of a scratch set (waits for that frame's rasteriser part). Returns true
+// if it overflowed its span buffer - the frame is incomplete; the next allocation is large enough.
+bool span_overflowed(b200r_ctx* ctx, int set)
+{
+    b200r_ctx::RasterSet& R = ctx->rs[set];
+    if (!R.pending) return false;
+    cudaEventSynchronize(R.counted);
+    R.pending = false;
+    const unsigned need = *R.h_spanCount;
+    if (need <= R.rb.spanCapacity) return false;
+    unsigned cap = R.rb.spanCapacity;
+    while (cap < need) cap *= 2;
+    ctx->spanCapacityWanted = std::max(ctx->spanCapacityWanted, cap);
+    return true;
 }
 
 int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStream_t stream, FrameParams& fp, int scratchSet = 0)
@@ -243,44 +269,49 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
     case B200R_MODE_GOURAUD:
     case B200R_MODE_PHONG: {
         const size_t px = (size_t)fp.W * fp.n_rows;
-        if (ctx->zkey_pixels < px) {
-            if (ctx->rb.zkeys) cudaFree(ctx->rb.zkeys);
-            ctx->rb.zkeys = nullptr; ctx->zkey_pixels = 0;
-            CU(cudaMalloc((void**)&ctx->rb.zkeys, px * 8));
-            ctx->zkey_pixels = px;
+        if (scratchSet < 0 || scratchSet >= B200R_MAX_FRAMES_IN_FLIGHT) return fail(ctx, B200R_EINVAL, "scratch set out of range");
+        b200r_ctx::RasterSet& R = ctx->rs[scratchSet];
+        if (span_overflowed(ctx, scratchSet)) ctx->spanOverflowSticky = true;       // a frame nobody retried (stream / slot calls)
+        if (R.zkey_pixels < px) {
+            if (R.rb.zkeys) cudaFree(R.rb.zkeys);
+            R.rb.zkeys = nullptr; R.zkey_pixels = 0;
+            CU(cudaMalloc((void**)&R.rb.zkeys, px * 8));
+            R.zkey_pixels = px;
         }
         if (fp.mode >= B200R_MODE_PHONG && !ctx->sw.raster_inline_shade) {      // per-pixel lighting pass (default)
-            if (ctx->attr_pixels < px) {
-                if (ctx->d_attrs) cudaFree(ctx->d_attrs);
-                ctx->d_attrs = nullptr; ctx->attr_pixels = 0;
-                CU(cudaMalloc((void**)&ctx->d_attrs, px * 32));
-                ctx->attr_pixels = px;
+            if (R.attr_pixels < px) {
+                if (R.d_attrs) cudaFree(R.d_attrs);
+                R.d_attrs = nullptr; R.attr_pixels = 0;
+                CU(cudaMalloc((void**)&R.d_attrs, px * 32));
+                R.attr_pixels = px;
             }
-            ctx->rb.attrs = ctx->d_attrs;
-        } else ctx->rb.attrs = nullptr;
-        if (!ctx->rb.spans) {
-            ctx->rb.spanCapacity = 1u << 20;
-            CU(cudaMalloc((void**)&ctx->rb.spans, (size_t)ctx->rb.spanCapacity * 80));
+            R.rb.attrs = R.d_attrs;
+        } else R.rb.attrs = nullptr;
+        if (!R.rb.spanCount) {
+            CU(cudaMalloc((void**)&R.rb.spanCount, 64));
+            CU(cudaMallocHost((void**)&R.h_spanCount, 64));
+            CU(cudaEventCreateWithFlags(&R.counted, cudaEventDisableTiming));
         }
-        for (int attempt = 0;; attempt++) {
+        // The span buffer is sized up front (one 80-byte record per triangle and scanline it covers: 48 scanlines per triangle
+        // on average is far beyond any of the reference's models at 4K) and NOT read back inside the frame: the count follows the
+        // frame to pinned memory and is looked at when the frame is retired (blocking calls: the frame is simply rendered again
+        // with a larger buffer; stream / slot calls: reported by the next call).
+        const unsigned wantCap = std::max(ctx->spanCapacityWanted, std::max(1u << 20, 48u * ctx->sc.n_tris));
+        if (R.rb.spanCapacity < wantCap) {
+            if (R.rb.spans) cudaFree(R.rb.spans);
+            R.rb.spans = nullptr; R.rb.spanCapacity = 0;
+            CU(cudaMalloc((void**)&R.rb.spans, (size_t)wantCap * 80));
+            R.rb.spanCapacity = wantCap;
+        }
+        {
             int launches = 0;
-            CU(launch_raster(ctx->sc, fp, d_out, ctx->rb, ctx->d_ctr, ctx->counting, ctx->numSMs, stream, launches));
+            CU(launch_raster(ctx->sc, fp, d_out, R.rb, ctx->d_ctr, ctx->counting, ctx->numSMs, stream, launches));
             ctx->last_launches += (uint32_t)launches;
-            if (fp.mode <= B200R_MODE_POINTS_TRI) break;
-            // the span buffer is sized by doubling: a frame that overflowed is simply rendered again
-            CU(cudaMemcpyAsync(ctx->h_spanCount, ctx->rb.spanCount, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
-            CU(cudaStreamSynchronize(stream));
-            const unsigned need = *ctx->h_spanCount;
-            if (need <= ctx->rb.spanCapacity) break;
-            if (attempt >= 2) return fail(ctx, B200R_ENOMEM, "span buffer overflow persisted");
-            unsigned cap = ctx->rb.spanCapacity;
-            while (cap < need) cap *= 2;
-            cudaFree(ctx->rb.spans); ctx->rb.spans = nullptr;
-            CU(cudaMalloc((void**)&ctx->rb.spans, (size_t)cap * 80));
-            ctx->rb.spanCapacity = cap;
-            if (ctx->counting) CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(DeviceCounters), stream));
-            ctx->last_launches = 0;
-            CU(cudaEventRecord(ctx->ev0, stream));
+            if (fp.mode > B200R_MODE_POINTS_TRI) {
+                CU(cudaMemcpyAsync(R.h_spanCount, R.rb.spanCount, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+                CU(cudaEventRecord(R.counted, stream));
+                R.pending = true;
+            }
         }
         break;
     }
@@ -319,7 +350,7 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
     // Screen::ShowScreen's hook (reference src/Screen.h:130-137): MLAA over the finished frame. A row-sharded frame is
     // filtered after the all-gather instead (b200r_mlaa_device), because the filter needs the neighbouring rows.
     if ((fp.flags & B200R_F_MLAA) && fp.row_step == 1) {
-        int rc2 = mlaa_on(ctx, d_out, fp.W, fp.H, stream);
+        int rc2 = mlaa_on(ctx, d_out, fp.W, fp.H, stream, scratchSet);
         if (rc2) return rc2;
     }
     CU(cudaEventRecord(ctx->ev1, stream));
@@ -333,9 +364,9 @@ const SwitchName kSwitches[] = {
     {"monolithic_rt", &Switches::monolithic_rt}, {"no_prune", &Switches::no_prune}, {"no_fuse", &Switches::no_fuse},
     {"rt_legacy", &Switches::rt_legacy}, {"no_root_rect", &Switches::no_root_rect}, {"pool_small", &Switches::pool_small},
     {"split_depth", &Switches::split_depth}, {"raster_inline_shade", &Switches::raster_inline_shade}, {"mlaa_scan", &Switches::mlaa_scan},
-    {"mlaa_fullscan", &Switches::mlaa_fullscan}, {"mlaa_nobatch", &Switches::mlaa_nobatch},
+    {"mlaa_fullscan", &Switches::mlaa_fullscan}, {"mlaa_nobatch", &Switches::mlaa_nobatch}, {"mlaa_no_tma", &Switches::mlaa_no_tma},
     {"no_frame_overlap", &Switches::no_frame_overlap}, {"bvh_serial_split", &Switches::bvh_serial_split},
-    {"pool_stats", &Switches::pool_stats}, {"pool_policy", &Switches::pool_policy}, {"pool_no_scatter", &Switches::pool_no_scatter}, {"pool_occ4", &Switches::pool_occ4},
+    {"pool_stats", &Switches::pool_stats}, {"pool_policy", &Switches::pool_policy}, {"pool_no_scatter", &Switches::pool_no_scatter}, {"pool_occ4", &Switches::pool_occ4}, {"pool_tiles_per_warp", &Switches::pool_tiles_per_warp},
     {"pool_leaf_min", &Switches::pool_leaf_min}, {"pool_sort_min", &Switches::pool_sort_min}, {"pool_shade_min", &Switches::pool_shade_min},
     {"pool_refill_min", &Switches::pool_refill_min}, {"pool_low_water", &Switches::pool_low_water}, {"pool_dry", &Switches::pool_dry},
 };
@@ -383,7 +414,6 @@ int b200r_init(int device, b200r_ctx** out)
     ctx->tileCounters[0] = ctx->d_tileCounter;
     CU(cudaMalloc((void**)&ctx->d_ctr, sizeof(DeviceCounters)));
     CU(cudaMemset(ctx->d_ctr, 0, sizeof(DeviceCounters)));
-    CU(cudaMalloc((void**)&ctx->rb.spanCount, 64));
     CU(cudaMallocHost((void**)&ctx->h_spanCount, 64));
     CU(rt_pool_configure());
     for (const SwitchName& n : kSwitches) {      // defaults from the environment, read ONCE here - never on the per-frame path
@@ -409,7 +439,12 @@ void b200r_destroy(b200r_ctx* ctx)
         if (k) cudaFree(ctx->tileCounters[k]);
         if (ctx->rstream[k]) cudaStreamDestroy(ctx->rstream[k]);
     }
-    cudaFree(ctx->d_attrs); cudaFree(ctx->d_mlaaScratch); cudaFree(ctx->d_mlaaLines); cudaFree(ctx->d_tileProf); cudaFree(ctx->rb.spans); cudaFree(ctx->rb.spanCount); cudaFree(ctx->rb.zkeys); cudaFree(ctx->d_shadowKeys);
+    cudaFree(ctx->d_tileProf); cudaFree(ctx->d_shadowKeys);
+    for (auto& R : ctx->rs) {
+        cudaFree(R.rb.zkeys); cudaFree(R.rb.spans); cudaFree(R.rb.spanCount); cudaFree(R.d_attrs); cudaFree(R.d_mlaaScratch); cudaFree(R.d_mlaaLines);
+        if (R.h_spanCount) cudaFreeHost(R.h_spanCount);
+        if (R.counted) cudaEventDestroy(R.counted);
+    }
     if (ctx->h_spanCount) cudaFreeHost(ctx->h_spanCount);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (auto& S : ctx->slot) {
@@ -642,10 +677,15 @@ int b200r_render_device(b200r_ctx* ctx, const b200r_frame* f, void* dev_xrgb, vo
     FrameParams fp;
     int rc = b200r_wait(ctx);                   // frames of b200r_render_async still in flight use the same scratch buffers
     if (rc) return rc;
-    rc = render_common(ctx, f, (uint32_t*)dev_xrgb, s, fp);
-    if (rc) return rc;
-    if (!cuda_stream) {
+    for (int attempt = 0;; attempt++) {
+        rc = render_common(ctx, f, (uint32_t*)dev_xrgb, s, fp);
+        if (rc) return rc;
+        if (cuda_stream) break;
         CU(cudaStreamSynchronize(s));
+        if (!span_overflowed(ctx, 0)) break;
+        if (attempt >= 3) return fail(ctx, B200R_ENOMEM, "span buffer overflow persisted");
+    }
+    if (!cuda_stream) {
         CU(cudaEventElapsedTime(&ctx->last_total_ms, ctx->ev0, ctx->ev1));
         ctx->last_dominant_ms = ctx->last_total_ms;
     }
@@ -657,8 +697,12 @@ int b200r_render_device_slot(b200r_ctx* ctx, const b200r_frame* f, void* dev_xrg
     if (!ctx) return fail(nullptr, B200R_EINVAL, "NULL ctx");
     if (!dev_xrgb || !cuda_stream) return fail(ctx, B200R_EINVAL, "b200r_render_device_slot needs a device frame pointer and a stream");
     if (scratch_slot >= B200R_MAX_FRAMES_IN_FLIGHT) return fail(ctx, B200R_EINVAL, "scratch_slot out of range");
-    if (!f || !(f->mode == 0 || f->mode == B200R_MODE_RAYTRACE || f->mode == B200R_MODE_RAYTRACE_AA) || (f->flags & B200R_F_MLAA))
-        return fail(ctx, B200R_EINVAL, "b200r_render_device_slot: ray-tracing modes without MLAA only");
+    if (!f || f->mode == B200R_MODE_LINES)
+        return fail(ctx, B200R_EINVAL, "b200r_render_device_slot: every mode but 3 (the wireframe pass sizes its fragment buffer on the host)");
+    if (ctx->spanOverflowSticky) {
+        ctx->spanOverflowSticky = false;
+        return fail(ctx, B200R_ENOMEM, "an earlier rasterised frame overflowed its span buffer and is incomplete; the buffer has been enlarged - submit again");
+    }
     if (ctx->counting || ctx->tileProfile) return fail(ctx, B200R_ESTATE, "b200r_render_device_slot: counters / tile profile use one shared buffer; switch them off");
     CU(cudaSetDevice(ctx->device));
     for (auto& S : ctx->slot)
@@ -689,6 +733,17 @@ int retire_slot(b200r_ctx* ctx, b200r_ctx::AsyncSlot& S)
 {
     if (!S.inflight) return B200R_OK;
     CU(cudaEventSynchronize(S.copied));
+    if (span_overflowed(ctx, S.set)) {          // the frame's span buffer was too small: render it again, now, with the enlarged one
+        FrameParams fp;
+        for (int attempt = 0;; attempt++) {
+            int rc = render_common(ctx, &S.frame, S.d, ctx->stream, fp, S.set);
+            if (rc) return rc;
+            CU(cudaMemcpyAsync(S.staged ? S.staging : S.user, S.d, S.user_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            if (!span_overflowed(ctx, S.set)) break;
+            if (attempt >= 3) return fail(ctx, B200R_ENOMEM, "span buffer overflow persisted");
+        }
+    }
     if (S.staged) memcpy(S.user, S.staging, S.user_words * 4);
     S.inflight = false;
     return B200R_OK;
@@ -715,10 +770,14 @@ int b200r_render(b200r_ctx* ctx, const b200r_frame* f, uint32_t* host_xrgb)
         CU(cudaMallocHost((void**)&ctx->h_pinned, words * 4));
         ctx->pinned_words = words;
     }
-    rc = render_common(ctx, f, ctx->d_frame, ctx->stream, fp);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(direct ? host_xrgb : ctx->h_pinned, ctx->d_frame, words * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    for (int attempt = 0;; attempt++) {
+        rc = render_common(ctx, f, ctx->d_frame, ctx->stream, fp);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(direct ? host_xrgb : ctx->h_pinned, ctx->d_frame, words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (!span_overflowed(ctx, 0)) break;                 // the span buffer was too small: the frame is simply rendered again
+        if (attempt >= 3) return fail(ctx, B200R_ENOMEM, "span buffer overflow persisted");
+    }
     CU(cudaEventElapsedTime(&ctx->last_total_ms, ctx->ev0, ctx->ev1));
     ctx->last_dominant_ms = ctx->last_total_ms;
     if (!direct) memcpy(host_xrgb, ctx->h_pinned, words * 4);
@@ -757,11 +816,10 @@ int b200r_render_async(b200r_ctx* ctx, const b200r_frame* f, uint32_t* host_xrgb
         CU(cudaMallocHost((void**)&S.staging, words * 4));
         S.staging_words = words;
     }
-    // Ray-traced frames rotate over `depth` streams / scratch sets: frame i+1 starts while the last long rays of frame i
-    // are still being walked (the persistent kernel's CTAs retire one by one) and takes over the SMs they free.
-    // Everything else (and any profiling / counting run) stays on the one stream and is therefore serialised.
-    const bool overlap = (fp.mode == B200R_MODE_RAYTRACE || fp.mode == B200R_MODE_RAYTRACE_AA) && !ctx->counting && !ctx->tileProfile &&
-                         !ctx->sw.no_frame_overlap && !(f->flags & B200R_F_MLAA);
+    // Frames rotate over `depth` streams / scratch sets: frame i+1 starts while the tail of frame i is still running and takes
+    // over the SMs it frees. Mode 3 (its fragment buffer is sized on the host) and profiling / counting runs stay on the one
+    // stream and are therefore serialised.
+    const bool overlap = fp.mode != B200R_MODE_LINES && !ctx->counting && !ctx->tileProfile && !ctx->sw.no_frame_overlap;
     const int set = overlap ? (int)(ctx->asyncIdx % ctx->depth) : 0;
     if (set && !ctx->rstream[set]) CU(cudaStreamCreateWithFlags(&ctx->rstream[set], cudaStreamNonBlocking));
     cudaStream_t rs = set ? ctx->rstream[set] : ctx->stream;
@@ -771,7 +829,7 @@ int b200r_render_async(b200r_ctx* ctx, const b200r_frame* f, uint32_t* host_xrgb
     CU(cudaStreamWaitEvent(ctx->copyStream, S.rendered, 0));
     CU(cudaMemcpyAsync(S.staged ? S.staging : host_xrgb, S.d, words * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
     CU(cudaEventRecord(S.copied, ctx->copyStream));
-    S.user = host_xrgb; S.user_words = words; S.inflight = true;
+    S.user = host_xrgb; S.user_words = words; S.inflight = true; S.frame = *f; S.set = set;
     ctx->asyncIdx++;
     return B200R_OK;
 }

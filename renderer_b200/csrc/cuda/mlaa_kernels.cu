@@ -11,6 +11,8 @@
 //   * separation lines of one row cover disjoint pixel ranges and only read/write inside them    -> one thread per line
 //   * all decisions (flags, split heights) read the immutable scratch copy only.
 // Float maths as in the reference (mixColor's float products + x86 byte truncation), -fmad=false.
+#include <cuda.h>          // CUtensorMap (types only: the driver entry point is looked up at run time)
+
 #include "device_types.cuh"
 #include "rt_kernels.cuh"
 #include "../mlaa_steps.h"
@@ -240,6 +242,118 @@ mlaa_blend_lines_kernel(uint32_t* fbi, const uint32_t* __restrict__ fb0, int res
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Vertical blending with the strip staged in shared memory by TMA.
+// A vertical separation line is walked DOWN a column: consecutive pixels are one row pitch apart (15 KB at 4K), so in
+// mlaa_blend_lines_kernel every step of every line is its own 32-byte sector out of L2. One job only ever touches its 8 columns
+// and one neighbour column on each side, so the CTA of a job pulls the whole 16-column strip (x0-4 .. x0+11, all rows:
+// 64 bytes per row, 138 KB at 2160 rows) into shared memory with cp.async.bulk.tensor.2d boxes of 16 x 128 pixels that all
+// complete on one mbarrier, runs the very same blends there (a record's pixel indices are re-based to the strip: row * 16 +
+// column - x0), and writes the strip back with cp.async.bulk.tensor stores. Jobs of one parity own disjoint 16-column strips
+// (the other columns of a strip are written back unchanged; the job at the left edge uses a 12-column strip from column 0),
+// so the reference's job order - even jobs, odd jobs, columns of a
+// job in order, one thread per line - is kept and the frame is bit-identical. Rows past the frame / columns left of it are
+// zero-filled on load and clipped on store by the TMA unit.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int STRIP_W = 16, STRIP_BOX_ROWS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ int strip_index(int g, int resX, int x0, int sw)
+{
+    const int y = g / resX;
+    return y * sw + (g - y * resX) - x0;
+}
+
+template <int BATCH>
+__global__ void __launch_bounds__(256)
+mlaa_blend_vstrip_tma_kernel(const __grid_constant__ CUtensorMap frameMap, const __grid_constant__ CUtensorMap firstMap, int resX, int resY,
+                             int yodd, const LineRec* __restrict__ rec, const int* __restrict__ cnt, int cap, int nBoxes)
+{
+    extern __shared__ __align__(128) uint32_t strip[];
+    __shared__ __align__(8) unsigned long long bar;
+    const int col0 = (2 * (int)blockIdx.x + yodd) * 8;            // first column of the job
+    int colEnd = col0 + 8;
+    if (colEnd >= resX) colEnd = resX - 1;                         // (rlast >= resy -> resy - 1, as in mlaa_blend_lines_kernel)
+    // The job at the left edge has no columns to its left: its strip is columns 0..11 (a second tensor map with 12-pixel boxes) -
+    // a TMA STORE must not start at a negative coordinate, and a 16-wide strip from 0 would overlap the next job's.
+    const bool first = col0 == 0;
+    const int x0 = first ? 0 : col0 - 4, sw = first ? STRIP_W - 4 : STRIP_W;
+    const uint32_t barAddr = smem_u32(&bar), stripAddr = smem_u32(strip);
+    const unsigned long long mapAddr = reinterpret_cast<unsigned long long>(first ? &firstMap : &frameMap);
+    const uint32_t boxBytes = (uint32_t)sw * STRIP_BOX_ROWS * 4;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barAddr), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"(boxBytes * (uint32_t)nBoxes) : "memory");
+        for (int k = 0; k < nBoxes; k++)
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                         ::"r"(stripAddr + (uint32_t)k * boxBytes), "l"(mapAddr), "r"(barAddr), "r"(x0), "r"(k * STRIP_BOX_ROWS) : "memory");
+    }
+    {   // every thread waits for the strip (phase 0 of the barrier)
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(barAddr), "r"(0) : "memory");
+    }
+    for (int col = col0; col < colEnd; col++) {
+        const int befor = col ? -1 : 0;
+        const int n = min(cnt[col], cap);
+        const LineRec* rr = rec + (size_t)col * cap;
+        for (int i = (int)threadIdx.x; i < n; i += (int)blockDim.x) {
+            LineRec r = rr[i];
+            if (r.ui0 >= 0) r.ui0 = strip_index(r.ui0, resX, x0, sw);  // -1: no such end point
+            if (r.ui1 >= 0) r.ui1 = strip_index(r.ui1, resX, x0, sw);  // -2: one-pixel line, -1: none
+            if (r.li0 >= 0) r.li0 = strip_index(r.li0, resX, x0, sw);
+            if (r.li1 >= 0) r.li1 = strip_index(r.li1, resX, x0, sw);
+            mlaa_line_blend<BATCH>(strip, r, sw, befor, 1);
+        }
+        __syncthreads();
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the generic-proxy writes above, before the async-proxy reads below
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < nBoxes; k++)
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(mapAddr), "r"(stripAddr + (uint32_t)k * boxBytes), "r"(x0), "r"(k * STRIP_BOX_ROWS) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && p) fn = (EncodeTiledFn)p;
+        else cudaGetLastError();
+    }
+    return fn;
+}
+
+// The frame as a 2-D tensor of 32-bit pixels, boxes of 16 x 128. false: no TMA path for this frame (caller uses the plain kernel).
+bool make_frame_map(CUtensorMap* map, uint32_t* d_frame, int resX, int resY, int boxW = STRIP_W)
+{
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || (reinterpret_cast<uintptr_t>(d_frame) & 15u) || (resX % 4)) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)resX, (cuuint64_t)resY};
+    const cuuint64_t strides[1] = {(cuuint64_t)resX * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)boxW, STRIP_BOX_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, d_frame, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace
 
 size_t mlaa_lines_bytes(int resX, int resY)
@@ -281,8 +395,25 @@ cudaError_t launch_mlaa(uint32_t* d_frame, uint32_t* d_scratch, int resX, int re
         auto blend = batch ? mlaa_blend_lines_kernel<BLEND_BATCH> : mlaa_blend_lines_kernel<1>;
         if (h0 > 0) blend<<<h0, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 0, 0, recH, cntH, endH, capH);
         if (h1 > 0) blend<<<h1, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 0, 1, recH, cntH, endH, capH);
-        if (v0 > 0) blend<<<v0, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 1, 0, recV, cntV, endV, capV);
-        if (v1 > 0) blend<<<v1, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 1, 1, recV, cntV, endV, capV);
+        // vertical jobs: the 16-column strip of a job staged in shared memory by TMA when it fits (else / mlaa_no_tma: walked in L2)
+        const int nBoxes = (resY + STRIP_BOX_ROWS - 1) / STRIP_BOX_ROWS;
+        const size_t stripBytes = (size_t)nBoxes * STRIP_BOX_ROWS * STRIP_W * 4;
+        CUtensorMap map, map12;
+        if (!sw.mlaa_no_tma && stripBytes <= 200 * 1024 && resX >= 32 && make_frame_map(&map, d_frame, resX, resY) &&
+            make_frame_map(&map12, d_frame, resX, resY, STRIP_W - 4)) {
+            auto vstrip = batch ? mlaa_blend_vstrip_tma_kernel<BLEND_BATCH> : mlaa_blend_vstrip_tma_kernel<1>;
+            static bool attr[2] = {false, false};
+            if (!attr[batch ? 1 : 0]) {
+                cudaError_t e = cudaFuncSetAttribute(vstrip, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                if (e != cudaSuccess) return e;
+                attr[batch ? 1 : 0] = true;
+            }
+            if (v0 > 0) vstrip<<<v0, 256, stripBytes, st>>>(map, map12, resX, resY, 0, recV, cntV, capV, nBoxes);
+            if (v1 > 0) vstrip<<<v1, 256, stripBytes, st>>>(map, map12, resX, resY, 1, recV, cntV, capV, nBoxes);
+        } else {
+            if (v0 > 0) blend<<<v0, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 1, 0, recV, cntV, endV, capV);
+            if (v1 > 0) blend<<<v1, 256, 0, st>>>(d_frame, d_scratch, resX, resY, 1, 1, recV, cntV, endV, capV);
+        }
         launches += 7;
         return cudaGetLastError();
     }

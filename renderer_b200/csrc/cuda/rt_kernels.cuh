@@ -18,10 +18,12 @@ struct Switches {
     int mlaa_scan = 0;            // row-scanning MLAA kernels instead of the two-stage path
     int mlaa_fullscan = 0;        // two-stage MLAA, lines walked by the scanning thread
     int mlaa_nobatch = 0;         // MLAA walks load one word per step
+    int mlaa_no_tma = 0;          // vertical MLAA blends walk the frame in L2 instead of a TMA-staged strip in shared memory
     int no_frame_overlap = 0;     // b200r_render_async keeps ray-traced frames on one stream
     int bvh_serial_split = 0;     // BVH build: one thread per node in every level
     int pool_policy = 0;          // rt_pool_kernel: how the inner pool is popped (rt_pool.cu PoolParams)
     int pool_leaf_min = 0, pool_sort_min = 0, pool_shade_min = 0, pool_refill_min = 0, pool_low_water = 0, pool_dry = 0;   // rt_pool_kernel thresholds (0 = built-in)
+    int pool_tiles_per_warp = 0;  // rt_pool_kernel: grid sized for this many 8x4 tiles per warp (0 = built-in 4)
     int pool_occ4 = 0;            // rt_pool_kernel: 4 CTAs per SM (64 registers, 256-entry pools) instead of 3
     int pool_no_scatter = 0;      // rt_pool_kernel: deal whole 8x4 tiles to warps (centre-out) instead of scattered 4-pixel groups
     int pool_stats = 0;           // rt_pool_kernel adds its per-phase iteration / lane counts to the work counters (tools/pool_stats.py)

@@ -581,7 +581,12 @@ cudaError_t launch_rt_pool(const DeviceScene& sc, const FrameParams& fp, uint32_
         k = fused ? rt_pool_kernel<true, 256, false, 4> : rt_pool_kernel<false, 256, false, 4>; smem = sizeof(WarpPool<256>) * POOL_WARPS; ctas = 4;
     }
     int grid = numSMs * ctas;
-    const int needed = (pp.tiles.z * pp.tiles.w + POOL_WARPS - 1) / POOL_WARPS;       // one tile per warp is the least a warp can take
+    // Grid: one tile per warp is the least a warp can take, and a frame rendered alone is latency-bound - every warp that can take rays
+    // shortens it (a rank's 1/8 of C2's rows, kernel alone: 1 tile per warp 0.146 ms, 4: 0.235, 16: 0.69). A rank of a many-GPU job
+    // keeps several frames in flight instead: 4 tiles per warp leave room for the kernels of 3 frames on every SM (8 x B200, 4 frames
+    // in flight per rank: 8263 fps).
+    const int tpw = sw.pool_tiles_per_warp > 0 ? sw.pool_tiles_per_warp : (fp.row_step >= 4 ? 4 : 1);
+    const int needed = (pp.tiles.z * pp.tiles.w + POOL_WARPS * tpw - 1) / (POOL_WARPS * tpw);
     if (grid > needed) grid = needed;
     k<<<grid, POOL_WARPS * 32, smem, stream>>>(sc, fp, d_out, pixelCounter, pp, reinterpret_cast<HitRecord*>(hits), hitCount, stats);
     launches += 1;

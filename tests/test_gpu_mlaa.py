@@ -38,6 +38,9 @@ def test_mlaa_vs_oracle(rb, pyport, load_scene, gpu, model, mode, size):
     with gpu.switch("mlaa_fullscan"):
         full = gpu.render(f)                             # two-stage, but the scanning thread also walks the line it finds
     assert np.array_equal(got, full)
+    with gpu.switch("mlaa_no_tma"):
+        in_l2 = gpu.render(f)                            # vertical blends walked in L2 instead of a TMA-staged strip in shared memory
+    assert np.array_equal(got, in_l2)
     with gpu.switch("mlaa_nobatch"):
         stepwise = gpu.render(f)                         # flag / pixel words loaded one step at a time, as the reference's loops do
     assert np.array_equal(got, stepwise)

@@ -115,3 +115,41 @@ def test_wireframe_full_size(rb, pyport, load_scene, gpu, model, size):
     for r in range(2):
         part = gpu.render(rb.make_frame(3, size[0], size[1], cam, row_first=r, row_step=2))
         assert np.array_equal(part, got[r::2])
+
+
+def test_rasterised_frames_in_flight_equal_blocking_frames(rb, load_scene, gpu):
+    """Raster modes rotate over scratch sets / streams like ray-traced frames do (b200r_render_async, b200r_pipeline): nothing is
+    read back inside a frame any more. Frames of several modes - with and without MLAA - submitted back to back must each
+    equal the blocking call's frame, through render_async and through a 3-deep pipeline."""
+    import numpy as np
+    import torch
+    s = load_scene("statue.ply")
+    gpu.upload(s)
+    gpu.render_shadowmap(0, rb.default_light_pos(0))
+    cams = rb.Orbit.cameras(range(10))
+    specs = [(6, 1280, 720, rb.F_DEFAULT | rb.F_MLAA), (5, 1280, 720, rb.F_DEFAULT), (6, 1280, 720, rb.F_DEFAULT | rb.F_MLAA),
+             (4, 800, 600, rb.F_DEFAULT), (8, 1280, 720, rb.F_DEFAULT | rb.F_MLAA), (2, 640, 480, rb.F_DEFAULT),
+             (6, 1280, 720, rb.F_DEFAULT | rb.F_MLAA), (7, 1280, 720, rb.F_DEFAULT), (1, 640, 480, rb.F_DEFAULT),
+             (6, 1280, 720, rb.F_DEFAULT | rb.F_MLAA)]
+    frames = [rb.make_frame(m, w, h, cams[k], flags=fl, frame_index=k) for k, (m, w, h, fl) in enumerate(specs)]
+    want = [gpu.render(f).copy() for f in frames]
+    for depth in (2, 3):
+        gpu.set_pipeline_depth(depth)
+        outs = [torch.zeros((f.height, f.width), dtype=torch.int32).pin_memory().numpy().view(np.uint32) for f in frames]
+        for f, o in zip(frames, outs):
+            gpu.render_async(f, o)
+        gpu.wait()
+        for k in range(len(frames)):
+            assert np.array_equal(outs[k], want[k]), f"render_async depth {depth}, frame {k} (mode {specs[k][0]})"
+    gpu.set_pipeline_depth(2)
+    same = [k for k, sp in enumerate(specs) if sp[:3] == (6, 1280, 720)]
+    pipe = rb.Pipeline(gpu, 1280, 720, depth=3)
+    try:
+        hosts = [torch.zeros((720, 1280), dtype=torch.int32).pin_memory() for _ in same]
+        for k, h in zip(same, hosts):
+            pipe.submit(frames[k], h.data_ptr())
+        pipe.drain()
+        for k, h in zip(same, hosts):
+            assert np.array_equal(h.numpy().view(np.uint32), want[k]), f"pipeline frame {k}"
+    finally:
+        pipe.close()
