@@ -83,6 +83,7 @@ struct b200r_ctx {
         void* d_mlaaLines = nullptr; size_t mlaaLinesBytes = 0;
     } rs[B200R_MAX_FRAMES_IN_FLIGHT];
     unsigned spanCapacityWanted = 0;              // grows when a frame overflowed
+    bool framesInFlight = false;                  // the frame being enqueued is one of several in flight (set by the slot / async calls)
     bool spanOverflowSticky = false;              // an un-retried frame overflowed its span buffer (device / slot calls)
     WireBuffers wb{};
     unsigned* h_spanCount = nullptr;          // pinned (mode 3: fragment count)
@@ -239,7 +240,7 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
             const size_t px32 = (size_t)nTiles * 32;
             if (scratchSet < 0 || scratchSet >= B200R_MAX_FRAMES_IN_FLIGHT) return fail(ctx, B200R_EINVAL, "scratch set out of range");
             RtBuffers& rt = ctx->rts[scratchSet];
-            if (!ctx->tileCounters[scratchSet]) CU(cudaMalloc((void**)&ctx->tileCounters[scratchSet], 64));
+            if (!ctx->tileCounters[scratchSet]) CU(cudaMalloc((void**)&ctx->tileCounters[scratchSet], 64 * sizeof(unsigned)));
             if (rt.pixels < px32) {
                 cudaFree(rt.hits); rt.hits = nullptr; rt.pixels = 0;
                 CU(cudaMalloc((void**)&rt.hits, px32 * 32));             // one 32-byte hit record per pixel at most
@@ -252,6 +253,30 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
                 rt.legacyPixels = px32;
             }
             rt.counters = ctx->tileCounters[scratchSet];
+            rt.inFlight = ctx->framesInFlight;
+            {   // wavefront buffers of the generic configurations (AO / reflections / two lights), sized on first use
+                const bool simple = fp.n_lights == 1 && !(fp.flags & (B200R_F_REFLECTIONS | B200R_F_AO));
+                const unsigned stride = ((fp.flags & B200R_F_AO) ? fp.ao_samples : 0u) + ((fp.flags & B200R_F_SHADOWS) ? fp.n_lights : 0u);
+                if ((!simple || ctx->sw.no_fuse) && !ctx->sw.no_wavefront && !ctx->counting && fp.mode == B200R_MODE_RAYTRACE && fp.max_depth <= 3 &&
+                    (rt.wfPixels < px32 || rt.wfStride < stride)) {
+                    cudaFree(rt.wfHits1); cudaFree(rt.wfHits2); cudaFree(rt.wfPaths); cudaFree(rt.wfRefl);
+                    cudaFree(rt.wfRays); cudaFree(rt.wfOcc); cudaFree(rt.wfCos); cudaFree(rt.wfCtx);
+                    rt.wfHits1 = rt.wfHits2 = rt.wfPaths = nullptr; rt.wfRefl = rt.wfRays = rt.wfCtx = nullptr; rt.wfOcc = nullptr; rt.wfCos = nullptr;
+                    rt.wfPixels = 0;
+                    const size_t cap = std::max(px32, rt.pixels);
+                    // hits are processed in chunks of at most 1 Mi (at most 16 chunks per level: very large frames get larger chunks)
+                    const unsigned chunk = (unsigned)std::min<size_t>(cap, std::max<size_t>((size_t)1 << 20, (cap + 15) / 16));
+                    const unsigned st = std::max(stride, std::max(rt.wfStride, 1u));
+                    CU(cudaMalloc(&rt.wfHits1, cap * 32)); CU(cudaMalloc(&rt.wfHits2, cap * 32));
+                    CU(cudaMalloc(&rt.wfPaths, cap * wavefront_path_bytes()));
+                    CU(cudaMalloc((void**)&rt.wfRefl, cap * 48));
+                    CU(cudaMalloc((void**)&rt.wfRays, (size_t)chunk * st * 48));
+                    CU(cudaMalloc((void**)&rt.wfOcc, (size_t)chunk * st));
+                    CU(cudaMalloc((void**)&rt.wfCos, (size_t)chunk * st * 4));
+                    CU(cudaMalloc((void**)&rt.wfCtx, (size_t)chunk * 16));
+                    rt.wfPixels = cap; rt.wfChunk = chunk; rt.wfStride = st;
+                }
+            }
             int launches = 0;
             CU(launch_raytrace(ctx->sc, fp, d_out, rt, ctx->sw, ctx->d_ctr, ctx->counting, prof, ctx->numSMs, stream, launches));
             ctx->last_launches += (uint32_t)launches;
@@ -361,12 +386,12 @@ int render_common(b200r_ctx* ctx, const b200r_frame* f, uint32_t* d_out, cudaStr
 
 struct SwitchName { const char* name; int Switches::*field; };
 const SwitchName kSwitches[] = {
-    {"monolithic_rt", &Switches::monolithic_rt}, {"no_prune", &Switches::no_prune}, {"no_fuse", &Switches::no_fuse},
+    {"monolithic_rt", &Switches::monolithic_rt}, {"no_prune", &Switches::no_prune}, {"no_fuse", &Switches::no_fuse}, {"no_wavefront", &Switches::no_wavefront},
     {"rt_legacy", &Switches::rt_legacy}, {"no_root_rect", &Switches::no_root_rect}, {"pool_small", &Switches::pool_small},
     {"split_depth", &Switches::split_depth}, {"raster_inline_shade", &Switches::raster_inline_shade}, {"mlaa_scan", &Switches::mlaa_scan},
     {"mlaa_fullscan", &Switches::mlaa_fullscan}, {"mlaa_nobatch", &Switches::mlaa_nobatch}, {"mlaa_no_tma", &Switches::mlaa_no_tma},
     {"no_frame_overlap", &Switches::no_frame_overlap}, {"bvh_serial_split", &Switches::bvh_serial_split},
-    {"pool_stats", &Switches::pool_stats}, {"pool_policy", &Switches::pool_policy}, {"pool_no_scatter", &Switches::pool_no_scatter}, {"pool_occ4", &Switches::pool_occ4}, {"pool_tiles_per_warp", &Switches::pool_tiles_per_warp},
+    {"pool_stats", &Switches::pool_stats}, {"pool_policy", &Switches::pool_policy}, {"pool_scatter", &Switches::pool_scatter}, {"pool_occ3", &Switches::pool_occ3}, {"pool_tiles_per_warp", &Switches::pool_tiles_per_warp},
     {"pool_leaf_min", &Switches::pool_leaf_min}, {"pool_sort_min", &Switches::pool_sort_min}, {"pool_shade_min", &Switches::pool_shade_min},
     {"pool_refill_min", &Switches::pool_refill_min}, {"pool_low_water", &Switches::pool_low_water}, {"pool_dry", &Switches::pool_dry},
 };
@@ -410,7 +435,7 @@ int b200r_init(int device, b200r_ctx** out)
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&ctx->ev0)); CU(cudaEventCreate(&ctx->ev1));
-    CU(cudaMalloc((void**)&ctx->d_tileCounter, 64));
+    CU(cudaMalloc((void**)&ctx->d_tileCounter, 64 * sizeof(unsigned)));
     ctx->tileCounters[0] = ctx->d_tileCounter;
     CU(cudaMalloc((void**)&ctx->d_ctr, sizeof(DeviceCounters)));
     CU(cudaMemset(ctx->d_ctr, 0, sizeof(DeviceCounters)));
@@ -436,6 +461,7 @@ void b200r_destroy(b200r_ctx* ctx)
     for (int k = 0; k < B200R_MAX_FRAMES_IN_FLIGHT; k++) {
         RtBuffers& rt = ctx->rts[k];
         cudaFree(rt.queue); cudaFree(rt.hits); cudaFree(rt.keys);
+        cudaFree(rt.wfHits1); cudaFree(rt.wfHits2); cudaFree(rt.wfPaths); cudaFree(rt.wfRefl); cudaFree(rt.wfRays); cudaFree(rt.wfOcc); cudaFree(rt.wfCos); cudaFree(rt.wfCtx);
         if (k) cudaFree(ctx->tileCounters[k]);
         if (ctx->rstream[k]) cudaStreamDestroy(ctx->rstream[k]);
     }
@@ -708,7 +734,10 @@ int b200r_render_device_slot(b200r_ctx* ctx, const b200r_frame* f, void* dev_xrg
     for (auto& S : ctx->slot)
         if (S.inflight) return fail(ctx, B200R_ESTATE, "b200r_render_device_slot while b200r_render_async frames are in flight (b200r_wait first)");
     FrameParams fp;
-    return render_common(ctx, f, (uint32_t*)dev_xrgb, (cudaStream_t)cuda_stream, fp, (int)scratch_slot);
+    ctx->framesInFlight = true;
+    const int rc = render_common(ctx, f, (uint32_t*)dev_xrgb, (cudaStream_t)cuda_stream, fp, (int)scratch_slot);
+    ctx->framesInFlight = false;
+    return rc;
 }
 
 int b200r_set_pipeline_depth(b200r_ctx* ctx, uint32_t depth)
@@ -823,7 +852,9 @@ int b200r_render_async(b200r_ctx* ctx, const b200r_frame* f, uint32_t* host_xrgb
     const int set = overlap ? (int)(ctx->asyncIdx % ctx->depth) : 0;
     if (set && !ctx->rstream[set]) CU(cudaStreamCreateWithFlags(&ctx->rstream[set], cudaStreamNonBlocking));
     cudaStream_t rs = set ? ctx->rstream[set] : ctx->stream;
+    ctx->framesInFlight = overlap && ctx->depth > 1;
     rc = render_common(ctx, f, S.d, rs, fp, set);
+    ctx->framesInFlight = false;
     if (rc) return rc;
     CU(cudaEventRecord(S.rendered, rs));
     CU(cudaStreamWaitEvent(ctx->copyStream, S.rendered, 0));

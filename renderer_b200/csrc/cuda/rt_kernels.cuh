@@ -9,7 +9,8 @@ namespace b200r {
 struct Switches {
     int monolithic_rt = 0;        // rt_frame_kernel for every ray-traced frame
     int no_prune = 0;             // no distance pruning in the closest-hit traversal
-    int no_fuse = 0;              // simple configuration through hit records + rt_shade_kernel as well
+    int no_fuse = 0;              // simple configuration through hit records + the generic route as well
+    int no_wavefront = 0;         // generic configurations: rt_shade_kernel (one thread per hit walks every secondary ray) instead of the wavefront
     int rt_legacy = 0;            // round 1's job pipeline (rt_rootcull_kernel + rt_primary_kernel) instead of rt_pool_kernel
     int no_root_rect = 0;         // no screen rectangle around the root box: every pixel's ray is built
     int pool_small = 0;           // 128-entry pools: exercises the overflow guard of rt_pool_kernel
@@ -24,8 +25,8 @@ struct Switches {
     int pool_policy = 0;          // rt_pool_kernel: how the inner pool is popped (rt_pool.cu PoolParams)
     int pool_leaf_min = 0, pool_sort_min = 0, pool_shade_min = 0, pool_refill_min = 0, pool_low_water = 0, pool_dry = 0;   // rt_pool_kernel thresholds (0 = built-in)
     int pool_tiles_per_warp = 0;  // rt_pool_kernel: grid sized for this many 8x4 tiles per warp (0 = built-in 4)
-    int pool_occ4 = 0;            // rt_pool_kernel: 4 CTAs per SM (64 registers, 256-entry pools) instead of 3
-    int pool_no_scatter = 0;      // rt_pool_kernel: deal whole 8x4 tiles to warps (centre-out) instead of scattered 4-pixel groups
+    int pool_occ3 = 0;            // rt_pool_kernel: C2-type frames with 3 CTAs per SM (76 registers, 512-entry pools) instead of 4
+    int pool_scatter = 0;         // rt_pool_kernel: 0 = scattered 4-pixel groups for a frame alone, whole 8x4 tiles for frames in flight; 1 / 2 force
     int pool_stats = 0;           // rt_pool_kernel adds its per-phase iteration / lane counts to the work counters (tools/pool_stats.py)
 };
 
@@ -39,6 +40,13 @@ struct RtBuffers {
     void* queue = nullptr;
     unsigned long long* keys = nullptr;
     size_t legacyPixels = 0;
+    // wavefront of the generic configurations (rt_wavefront.cu): hits of levels 1 and 2, one 64-byte path record per primary hit,
+    // reflection-ray records (one per hit), and per chunk of `wfChunk` hits: any-hit ray records (wfStride per hit), their result
+    // bytes, the AO cosines and the per-hit shading context
+    void* wfHits1 = nullptr; void* wfHits2 = nullptr; void* wfPaths = nullptr;
+    float4* wfRefl = nullptr; float4* wfRays = nullptr; unsigned char* wfOcc = nullptr; float* wfCos = nullptr; float4* wfCtx = nullptr;
+    size_t wfPixels = 0; unsigned wfChunk = 0, wfStride = 0;
+    bool inFlight = false;                    // this frame is one of several in flight (b200r_render_device_slot, b200r_render_async at depth > 1)
 };
 cudaError_t launch_raytrace(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, RtBuffers& rt, const Switches& sw,
                             DeviceCounters* d_ctr, bool count, unsigned long long* d_tileProf, int numSMs, cudaStream_t stream,
@@ -78,7 +86,13 @@ bool pool_supported(const DeviceScene& sc);
 cudaError_t rt_pool_configure();            // once per device: opt in to > 48 KB of dynamic shared memory
 cudaError_t launch_rt_pool(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, bool fused, bool prune, const Switches& sw,
                            unsigned* pixelCounter, void* hits, unsigned* hitCount, int numSMs, cudaStream_t stream, int& launches,
-                           DeviceCounters* stats = nullptr);
+                           DeviceCounters* stats = nullptr, bool inFlight = false);
+cudaError_t launch_rt_pool_queue(const DeviceScene& sc, const FrameParams& fp, bool anyhit, bool prune, const Switches& sw, unsigned* cursor,
+                                 const float4* rays, const unsigned* count, unsigned first, unsigned cap, unsigned stride,
+                                 unsigned char* occ, void* hits, unsigned* hitCount, int numSMs, cudaStream_t stream, int& launches);
+size_t wavefront_path_bytes();
+cudaError_t launch_rt_wavefront(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, RtBuffers& rt, const Switches& sw,
+                                bool prune, int numSMs, cudaStream_t stream, int& launches);
 cudaError_t launch_division_selftest(unsigned long long samples, uint32_t seed, unsigned long long* d_mismatches,
                                      float* d_firstBad, int numSMs, cudaStream_t stream);
 cudaError_t launch_deinterleave(const uint32_t* gathered, uint32_t* frame, uint32_t W, uint32_t H, uint32_t P,

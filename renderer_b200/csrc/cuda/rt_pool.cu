@@ -28,6 +28,8 @@
 //     against kernel arguments; the frame is cleared beforehand, so the 81 % of C2's pixels that miss are never touched.
 //   * The pool cannot overflow: when it is nearly full the top 32 entries are walked depth-first by their lanes with a private
 //     stack (same tests, same merges) instead of being expanded.
+#include <cstring>
+
 #include "rt_common.cuh"
 #include "rt_kernels.cuh"
 
@@ -40,9 +42,9 @@ constexpr int POOL_WARPS = 8;            // warps per CTA (independent of each o
 constexpr int POOL_CTAS_PER_SM = 3;
 constexpr int CAP_L = 128;               // leaf pool: < LEAF_MIN waiting + at most 64 pushed per inner iteration (+ 32 roots)
 // scheduling thresholds (defaults; developer switches pool_* override them for tuning)
-constexpr int LEAF_MIN = 32;             // run a leaf iteration as soon as this many leaves wait
+constexpr int LEAF_MIN = 24;             // run a leaf iteration as soon as this many leaves wait
 constexpr int SORT_MIN = 8;              // look at finished slots once this many wait (or the warp is running dry)
-constexpr int SHADE_MIN = 12;            // shade resolved hits once this many wait (or the warp is running dry)
+constexpr int SHADE_MIN = 16;            // shade resolved hits once this many wait (or the warp is running dry)
 constexpr int REFILL_MIN = 8;            // take new pixels once this many slots are free ...
 constexpr int LOW_WATER = 32;            // ... and fewer than this many hot entries are pending
 constexpr int DRY = 16;                  // "running dry": fewer inner entries than this are pending
@@ -67,8 +69,9 @@ struct __align__(16) WarpPool {
     float4 rr[32];                       // slot: refined reciprocals of the direction, w = bits(triangle to skip): >= 0 marks a SHADOW ray
     unsigned long long key[32];          // slot: (bits(best hitZ) << 32) | list position; shadow slots: (bits(light distance^2) << 32)
     int pend[32];                        // slot: pool entries not yet processed
-    uint32_t pix[32];                    // slot: (packed row << 16) | x
+    uint32_t pix[32];                    // slot: (packed row << 16) | x; queue modes: where the ray's result goes
     uint32_t lit[32], shd[32];           // shadow slots: the two possible pixel words
+    float4 rl[32];                       // any-hit slots: the point the ray must reach (light / end of an AO ray)
 };
 
 __device__ __forceinline__ uint32_t make_item(uint32_t ref, uint32_t slot) { return (ref & ITEM_REF_MASK) | (slot << ITEM_SLOT_SHIFT); }
@@ -96,10 +99,9 @@ __device__ __forceinline__ bool box_fast(const float4& o, const float4& d, const
 
 // The triangles of one leaf against one ray, in list order (reference src/Raytracer.cc:235-298). Closest-hit rays fold
 // improving hits into `bestK`; shadow rays return true at the first triangle that is nearer to the light than the origin is.
-__device__ __forceinline__ bool intersect_leaf(const DeviceScene& sc, const V3& o, const V3& d, uint32_t li, int avoid,
+__device__ __forceinline__ bool intersect_leaf(const DeviceScene& sc, const V3& o, const V3& d, uint32_t li, int avoid, bool isShadow,
                                                const V3& lightPos, float lightDistSq, unsigned long long& bestK)
 {
-    const bool isShadow = avoid >= 0;
     const float4* rec = sc.leaftris + 5 * (size_t)li;
     for (;; rec += 5, li++) {
         const float4 q4 = __ldg(rec + 4), q0 = __ldg(rec + 0), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
@@ -145,7 +147,7 @@ __device__ __forceinline__ bool intersect_leaf(const DeviceScene& sc, const V3& 
 // Cold path: one lane walks a whole subtree depth-first with a private stack - the reference's own loop with near-first order
 // and pruning. Used for rays outside the shared-reciprocal domain (a zero direction component: they take the reference's
 // `dir == 0` rule, ray_box<false>) and when a pool is about to overflow. Results go where the pooled lanes put theirs.
-__device__ __noinline__ void walk_subtree(const DeviceScene& sc, const RayPrep rp, const int avoid, const V3 lightPos, uint32_t cur, float tcur,
+__device__ __noinline__ void walk_subtree(const DeviceScene& sc, const RayPrep rp, const int avoid, const bool anyhit, const V3 lightPos, uint32_t cur, float tcur,
                                           unsigned long long* key, const volatile float* slackWord)
 {
     uint32_t stk[B200R_BVH_STACK_SIZE]; float tst[B200R_BVH_STACK_SIZE];
@@ -158,7 +160,7 @@ __device__ __noinline__ void walk_subtree(const DeviceScene& sc, const RayPrep r
         if (cur != REF_EMPTY && !pruned(tcur, slack, best)) {
             if (cur & REF_LEAF) {
                 unsigned long long bestK = k0;
-                if (intersect_leaf(sc, rp.o, rp.d, cur & ITEM_INDEX_MASK, avoid, lightPos, best, bestK)) {
+                if (intersect_leaf(sc, rp.o, rp.d, cur & ITEM_INDEX_MASK, avoid, anyhit, lightPos, best, bestK)) {
                     *const_cast<float*>(slackWord) = -__int_as_float(0x7f800000);     // occluded: every other entry of the ray is dropped
                     return;
                 }
@@ -207,12 +209,27 @@ struct PoolParams {
     unsigned long long scatterInv;  //    of the frame instead of one tile (floor(2^64 / nGroups), for the modulo)
 };
 
+// Where the rays of a launch come from and where their results go (MODE):
+//   POOL_FUSED    the pixels of the frame; a resolved hit is shaded here and its slot re-armed as the hit's shadow ray (C2-type frames)
+//   POOL_PRIMARY  the pixels of the frame; resolved hits are appended to `hits` (generic configurations, level 0)
+//   POOL_ANYHIT   a queue of 48-byte ray records {origin, -}{direction, bits(triangle to skip)}{point to reach, bits(result index)}:
+//                 shadow and ambient-occlusion rays; `occ[result index]` becomes 1 if anything lies between origin and that point
+//   POOL_CLOSEST  the same records, closest hit wanted (reflection rays); hits are appended to `hits` tagged with the result index
+// Queue modes take the rays [0, min(queueCap, *queueCount - queueFirst) * queueStride) of `rays`.
+enum { POOL_FUSED = 0, POOL_PRIMARY = 1, POOL_ANYHIT = 2, POOL_CLOSEST = 3 };
+struct PoolQueue {
+    const float4* rays; const unsigned* count; unsigned first, cap, stride;
+    unsigned char* occ;
+};
+
 // STATS (developer switch pool_stats): per-phase iteration / lane counts are added to DeviceCounters (tools/pool_stats.py).
-template <bool FUSED, int CAP_I, bool STATS = false, int CTAS = POOL_CTAS_PER_SM>
+template <int MODE, int CAP_I, bool STATS = false, int CTAS = POOL_CTAS_PER_SM>
 __global__ void __launch_bounds__(POOL_WARPS * 32, CTAS)
 rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsigned* __restrict__ pixelCounter, PoolParams pp,
-               HitRecord* __restrict__ hits, unsigned* __restrict__ hitCount, DeviceCounters* __restrict__ stats)
+               HitRecord* __restrict__ hits, unsigned* __restrict__ hitCount, DeviceCounters* __restrict__ stats, PoolQueue q)
 {
+    constexpr bool FUSED = MODE == POOL_FUSED;
+    constexpr bool QUEUE = MODE == POOL_ANYHIT || MODE == POOL_CLOSEST;
     const int4 tiles = pp.tiles;
     const int prune = pp.prune, policy = pp.policy;
     const int LEAF_MIN = pp.leafMin, SORT_MIN = pp.sortMin, SHADE_MIN = pp.shadeMin, REFILL_MIN = pp.refillMin, LOW_WATER = pp.lowWater, DRY = pp.dry;
@@ -226,7 +243,11 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
     const V3 eye = mkv3(fp.eye[0], fp.eye[1], fp.eye[2]);
     const V3 lightPos = mkv3(fp.light_pos[0][0], fp.light_pos[0][1], fp.light_pos[0][2]);
     const int tx0 = tiles.x, ty0 = tiles.y, ntx = tiles.z, nty = tiles.w;
-    const unsigned total = (unsigned)(ntx * nty) * 32u;
+    unsigned total = (unsigned)(ntx * nty) * 32u;
+    if (QUEUE) {
+        const unsigned n = *q.count;
+        total = n > q.first ? min(q.cap, n - q.first) * q.stride : 0u;
+    }
     const float INF = __int_as_float(0x7f800000);
 
     // warp-uniform bookkeeping
@@ -250,8 +271,11 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
                 if (!pruned(__uint_as_float(it.y), ro.w, best)) {
                     const float4 rd = P.rd[slot];
                     unsigned long long bestK = k0;
+                    const int avoid = __float_as_int(P.rr[slot].w);
+                    const bool anyhit = MODE == POOL_ANYHIT || (FUSED && avoid >= 0);
+                    const float4 rl = P.rl[slot];
                     const bool occ = intersect_leaf(sc, mkv3(ro.x, ro.y, ro.z), mkv3(rd.x, rd.y, rd.z), it.x & ITEM_INDEX_MASK,
-                                                    __float_as_int(P.rr[slot].w), lightPos, best, bestK);
+                                                    avoid, anyhit, mkv3(rl.x, rl.y, rl.z), best, bestK);
                     if (occ) P.ro[slot].w = -INF;
                     else if (bestK < k0) atomicMin(&P.key[slot], bestK);
                 }
@@ -272,7 +296,10 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
             bool freed = false, hit = false; uint32_t slot = 0;
             if ((int)lane < ndone) {
                 slot = __fns(doneMask, 0u, (int)lane + 1);
-                if (__float_as_int(P.rr[slot].w) >= 0) {
+                if (MODE == POOL_ANYHIT) {
+                    if (P.ro[slot].w == -INF) q.occ[P.pix[slot]] = 1;
+                    freed = true;
+                } else if (FUSED && __float_as_int(P.rr[slot].w) >= 0) {
                     const uint32_t pix = P.pix[slot];
                     out[(size_t)(pix >> 16) * fp.W + (pix & 0xffffu)] = (P.ro[slot].w == -INF) ? P.shd[slot] : P.lit[slot];
                     freed = true;
@@ -296,8 +323,8 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
                 const size_t o = (size_t)(pix >> 16) * fp.W + (pix & 0xffffu);
                 freed = true;
                 const unsigned long long k = P.key[slot];
-                const float4 rd = P.rd[slot];
-                reconstruct_hit(sc, eye, mkv3(rd.x, rd.y, rd.z), (uint32_t)k, tri, hitp, kAB, kBC, kCA);
+                const float4 rd = P.rd[slot], ro = P.ro[slot];
+                reconstruct_hit(sc, mkv3(ro.x, ro.y, ro.z), mkv3(rd.x, rd.y, rd.z), (uint32_t)k, tri, hitp, kAB, kBC, kCA);
                 if (FUSED) {
                     uint32_t pixLit, pixShadow; V3 sdir; float ldsq;
                     shade_one_light(sc, fp, eye, tri, hitp, kAB, kBC, kCA, pixLit, pixShadow, sdir, ldsq);
@@ -315,6 +342,7 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
                             P.rd[slot] = make_float4(sdir.x, sdir.y, sdir.z, rp.fast ? 0.f : 1.f);
                             P.rr[slot] = make_float4(rp.r.x, rp.r.y, rp.r.z, __int_as_float(tri));
                             P.key[slot] = (unsigned long long)__float_as_uint(ldsq) << 32;
+                            P.rl[slot] = make_float4(lightPos.x, lightPos.y, lightPos.z, 0.f);
                             P.pend[slot] = 1; P.lit[slot] = pixLit; P.shd[slot] = pixShadow; freed = false; arm = true;
                         }
                     }
@@ -354,6 +382,18 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
             if (base + (unsigned)nfree >= total) exhausted = true;
             const unsigned g = base + lane;
             bool enter = false; RayPrep rp; int x = 0, r = 0;
+            int qAvoid = -1; uint32_t qResult = 0; V3 qTarget = eye;
+            if (QUEUE) {
+                if ((int)lane < nfree && g < total) {
+                    const float4* rec = q.rays + 3 * (size_t)g;
+                    const float4 a = __ldg(rec), b = __ldg(rec + 1), c = __ldg(rec + 2);
+                    qAvoid = __float_as_int(b.w); qResult = __float_as_uint(c.w); qTarget = mkv3(c.x, c.y, c.z);
+                    rp = prep_ray(sc, mkv3(a.x, a.y, a.z), mkv3(b.x, b.y, b.z));
+                    if (sc.root_ref & REF_LEAF) enter = (sc.root_ref != REF_EMPTY);
+                    else enter = rp.fast ? ray_box<true>(rp, sc.root_lo[0], sc.root_hi[0], sc.root_lo[1], sc.root_hi[1], sc.root_lo[2], sc.root_hi[2])
+                                         : ray_box<false>(rp, sc.root_lo[0], sc.root_hi[0], sc.root_lo[1], sc.root_hi[1], sc.root_lo[2], sc.root_hi[2]);
+                }
+            } else
             if ((int)lane < nfree && g < total) {
                 if (pp.scatterMul) {
                     const unsigned long long prod = (unsigned long long)(g >> 2) * pp.scatterMul;
@@ -383,16 +423,18 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
             if (enter) {
                 slot = __fns(freeMask, 0u, __popc(em & lt) + 1);
                 float slack = INF;
-                if (prune) {
+                if (prune && MODE != POOL_ANYHIT) {
                     // 1/|d| per axis (IEEE divide; +inf for a zero component switches pruning off for this ray)
                     const float m = fmaxf(fmaxf(1.0f / fabsf(rp.d.x), 1.0f / fabsf(rp.d.y)), 1.0f / fabsf(rp.d.z));
                     slack = 1e-4f * m + 1e-4f;
                 }
                 P.ro[slot] = make_float4(rp.o.x, rp.o.y, rp.o.z, slack);
                 P.rd[slot] = make_float4(rp.d.x, rp.d.y, rp.d.z, rp.fast ? 0.f : 1.f);
-                P.rr[slot] = make_float4(rp.r.x, rp.r.y, rp.r.z, __int_as_float(-1));
-                P.key[slot] = KEY_EMPTY;
-                P.pix[slot] = ((uint32_t)r << 16) | (uint32_t)x;
+                P.rr[slot] = make_float4(rp.r.x, rp.r.y, rp.r.z, __int_as_float(QUEUE ? qAvoid : -1));
+                // any-hit: "best" is the squared distance origin - target, as BVH_IntersectTriangles<true> starts (src/Raytracer.cc:212)
+                P.key[slot] = MODE == POOL_ANYHIT ? (unsigned long long)__float_as_uint(distancesq3(rp.o, qTarget)) << 32 : KEY_EMPTY;
+                if (MODE == POOL_ANYHIT) P.rl[slot] = make_float4(qTarget.x, qTarget.y, qTarget.z, 0.f);
+                P.pix[slot] = QUEUE ? qResult : (((uint32_t)r << 16) | (uint32_t)x);
                 P.pend[slot] = 1;
             }
             const unsigned pm = __ballot_sync(FULL, enter && !walked);
@@ -426,7 +468,8 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
             if (have) {
                 const float4 ro = P.ro[slot], rd = P.rd[slot], rr = P.rr[slot];
                 RayPrep rp; rp.o = mkv3(ro.x, ro.y, ro.z); rp.d = mkv3(rd.x, rd.y, rd.z); rp.r = mkv3(rr.x, rr.y, rr.z); rp.fast = rd.w == 0.f;
-                walk_subtree(sc, rp, __float_as_int(rr.w), lightPos, it.x & ITEM_REF_MASK, __uint_as_float(it.y), &P.key[slot], &P.ro[slot].w);
+                { const int avoid = __float_as_int(rr.w); const float4 rl = P.rl[slot];
+                  walk_subtree(sc, rp, avoid, MODE == POOL_ANYHIT || (FUSED && avoid >= 0), mkv3(rl.x, rl.y, rl.z), it.x & ITEM_REF_MASK, __uint_as_float(it.y), &P.key[slot], &P.ro[slot].w); }
                 fin = atomicSub(&P.pend[slot], 1) == 1;
             }
             doneMask |= __reduce_or_sync(FULL, fin ? (1u << slot) : 0u);
@@ -528,31 +571,25 @@ bool pool_supported(const DeviceScene& sc)
     return sc.n_nodes <= ITEM_INDEX_MASK && sc.n_list <= ITEM_INDEX_MASK;
 }
 
-cudaError_t rt_pool_configure()
+namespace {
+using PoolKernel = void (*)(DeviceScene, FrameParams, uint32_t*, unsigned*, PoolParams, HitRecord*, unsigned*, DeviceCounters*, PoolQueue);
+
+template <int MODE>
+PoolKernel pick_kernel(const Switches& sw, bool stats, size_t& smem, int& ctas)
 {
-    cudaError_t e = cudaSuccess;
-    const int big = (int)(sizeof(WarpPool<512>) * POOL_WARPS), small = (int)(sizeof(WarpPool<128>) * POOL_WARPS);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<true, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<false, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<true, 256, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpPool<256>) * POOL_WARPS));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<false, 256, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpPool<256>) * POOL_WARPS));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(rt_pool_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
-    return e;
+    ctas = POOL_CTAS_PER_SM;
+    if (sw.pool_small) { smem = sizeof(WarpPool<128>) * POOL_WARPS; return rt_pool_kernel<MODE, 128>; }
+    smem = sizeof(WarpPool<512>) * POOL_WARPS;
+    if (stats && MODE <= POOL_PRIMARY) return rt_pool_kernel<(MODE <= POOL_PRIMARY ? MODE : 0), 512, true>;
+    if (!sw.pool_occ3 && MODE == POOL_FUSED) {          // C2-type frames: 4 CTAs per SM (64 registers per thread, 256-entry pools): 0.339 ms vs 0.355 with 3
+        smem = sizeof(WarpPool<256>) * POOL_WARPS; ctas = 4;
+        return rt_pool_kernel<POOL_FUSED, 256, false, 4>;
+    }
+    return rt_pool_kernel<MODE, 512>;
 }
 
-cudaError_t launch_rt_pool(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, bool fused, bool prune, const Switches& sw,
-                           unsigned* pixelCounter, void* hits, unsigned* hitCount, int numSMs, cudaStream_t stream, int& launches,
-                           DeviceCounters* stats)
+void fill_thresholds(PoolParams& pp, const Switches& sw, bool prune)
 {
-    cudaError_t e = cudaMemsetAsync(d_out, 0, (size_t)fp.W * fp.n_rows * 4, stream);        // black; the kernel writes lit pixels only
-    if (e != cudaSuccess) return e;
-    const int4 bounds = sw.no_root_rect ? make_int4(0, 0, (int)fp.W - 1, (int)fp.H - 1) : root_screen_bounds(sc, fp);
-    PoolParams pp;
-    pp.tiles = tile_rect(fp, bounds);
-    if (pp.tiles.z <= 0 || pp.tiles.w <= 0) return cudaSuccess;
     pp.prune = prune ? 1 : 0;
     pp.policy = sw.pool_policy;
     pp.leafMin = sw.pool_leaf_min > 0 ? sw.pool_leaf_min : LEAF_MIN; pp.sortMin = sw.pool_sort_min > 0 ? sw.pool_sort_min : SORT_MIN;
@@ -560,10 +597,46 @@ cudaError_t launch_rt_pool(const DeviceScene& sc, const FrameParams& fp, uint32_
     pp.lowWater = sw.pool_low_water > 0 ? sw.pool_low_water : LOW_WATER; pp.dry = sw.pool_dry > 0 ? sw.pool_dry : DRY;
     if (pp.leafMin > 32) pp.leafMin = 32;             // the leaf pool holds < leafMin + 64 + 32 entries
     if (pp.lowWater > 64) pp.lowWater = 64;
+}
+}  // namespace
+
+cudaError_t rt_pool_configure()
+{
+    cudaError_t e = cudaSuccess;
+    const int big = (int)(sizeof(WarpPool<512>) * POOL_WARPS), small = (int)(sizeof(WarpPool<128>) * POOL_WARPS);
+    const int mid = (int)(sizeof(WarpPool<256>) * POOL_WARPS);
+    auto set = [&](PoolKernel k, int bytes) { if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); };
+    set(rt_pool_kernel<POOL_FUSED, 512>, big); set(rt_pool_kernel<POOL_PRIMARY, 512>, big);
+    set(rt_pool_kernel<POOL_ANYHIT, 512>, big); set(rt_pool_kernel<POOL_CLOSEST, 512>, big);
+    set(rt_pool_kernel<POOL_FUSED, 512, true>, big); set(rt_pool_kernel<POOL_PRIMARY, 512, true>, big);
+    set(rt_pool_kernel<POOL_FUSED, 128>, small); set(rt_pool_kernel<POOL_PRIMARY, 128>, small);
+    set(rt_pool_kernel<POOL_ANYHIT, 128>, small); set(rt_pool_kernel<POOL_CLOSEST, 128>, small);
+    set(rt_pool_kernel<POOL_FUSED, 256, false, 4>, mid);
+    return e;
+}
+
+// Primary rays of a frame: clears the frame, then the pooled kernel over the screen rectangle of the root box.
+cudaError_t launch_rt_pool(const DeviceScene& sc, const FrameParams& fp, uint32_t* d_out, bool fused, bool prune, const Switches& sw,
+                           unsigned* pixelCounter, void* hits, unsigned* hitCount, int numSMs, cudaStream_t stream, int& launches,
+                           DeviceCounters* stats, bool inFlight)
+{
+    cudaError_t e = cudaMemsetAsync(d_out, 0, (size_t)fp.W * fp.n_rows * 4, stream);        // black; the kernel writes lit pixels only
+    if (e != cudaSuccess) return e;
+    const int4 bounds = sw.no_root_rect ? make_int4(0, 0, (int)fp.W - 1, (int)fp.H - 1) : root_screen_bounds(sc, fp);
+    PoolParams pp;
+    pp.tiles = tile_rect(fp, bounds);
+    if (pp.tiles.z <= 0 || pp.tiles.w <= 0) return cudaSuccess;
+    fill_thresholds(pp, sw, prune);
     pp.nGroups = (unsigned)pp.tiles.z * 2u * (unsigned)pp.tiles.w * 4u;
     pp.groupsPerRow = (unsigned)pp.tiles.z * 2u;
     pp.scatterMul = 0; pp.scatterInv = 0;
-    if (!sw.pool_no_scatter && pp.nGroups > 64) {
+    // How pixels are dealt to warps. A frame rendered ALONE is bound by its slowest warp: scattered 4-pixel groups give every warp a
+    // cross-section of the frame (C2 kernel alone 0.355 ms vs 0.386 with whole tiles). A frame rendered with others IN FLIGHT is bound
+    // by throughput - the other frames fill the gaps - and whole 8x4 tiles keep a warp's rays coherent (2 frames in flight: 3850 fps
+    // vs 3170 scattered). pool_scatter = 1 / 2 forces scattered / whole tiles.
+    // (a rank's row shard of a many-GPU job stays scattered: few rays per warp, balance matters more - the measured 8-GPU setting)
+    const bool scatter = sw.pool_scatter == 1 || (sw.pool_scatter == 0 && (!inFlight || fp.row_step > 1));
+    if (scatter && pp.nGroups > 64) {
         // a multiplier near nGroups / golden ratio, coprime to nGroups: consecutive groups land far apart
         unsigned m = (unsigned)((double)pp.nGroups * 0.6180339887498949) | 1u;
         auto gcd = [](unsigned a, unsigned b) { while (b) { const unsigned t = a % b; a = b; b = t; } return a; };
@@ -571,15 +644,8 @@ cudaError_t launch_rt_pool(const DeviceScene& sc, const FrameParams& fp, uint32_
         pp.scatterMul = m % pp.nGroups;
         pp.scatterInv = ~0ull / pp.nGroups;
     }
-    using K = void (*)(DeviceScene, FrameParams, uint32_t*, unsigned*, PoolParams, HitRecord*, unsigned*, DeviceCounters*);
-    K k; size_t smem;
-    if (sw.pool_small) { k = fused ? rt_pool_kernel<true, 128> : rt_pool_kernel<false, 128>; smem = sizeof(WarpPool<128>) * POOL_WARPS; }
-    else { k = fused ? rt_pool_kernel<true, 512> : rt_pool_kernel<false, 512>; smem = sizeof(WarpPool<512>) * POOL_WARPS; }
-    if (stats && !sw.pool_small) k = fused ? rt_pool_kernel<true, 512, true> : rt_pool_kernel<false, 512, true>;
-    int ctas = POOL_CTAS_PER_SM;
-    if (sw.pool_occ4 && !sw.pool_small && !stats) {      // 4 CTAs per SM: 64 registers per thread, 256-entry pools
-        k = fused ? rt_pool_kernel<true, 256, false, 4> : rt_pool_kernel<false, 256, false, 4>; smem = sizeof(WarpPool<256>) * POOL_WARPS; ctas = 4;
-    }
+    size_t smem; int ctas;
+    PoolKernel k = fused ? pick_kernel<POOL_FUSED>(sw, stats != nullptr, smem, ctas) : pick_kernel<POOL_PRIMARY>(sw, stats != nullptr, smem, ctas);
     int grid = numSMs * ctas;
     // Grid: one tile per warp is the least a warp can take, and a frame rendered alone is latency-bound - every warp that can take rays
     // shortens it (a rank's 1/8 of C2's rows, kernel alone: 1 tile per warp 0.146 ms, 4: 0.235, 16: 0.69). A rank of a many-GPU job
@@ -588,7 +654,25 @@ cudaError_t launch_rt_pool(const DeviceScene& sc, const FrameParams& fp, uint32_
     const int tpw = sw.pool_tiles_per_warp > 0 ? sw.pool_tiles_per_warp : (fp.row_step >= 4 ? 4 : 1);
     const int needed = (pp.tiles.z * pp.tiles.w + POOL_WARPS * tpw - 1) / (POOL_WARPS * tpw);
     if (grid > needed) grid = needed;
-    k<<<grid, POOL_WARPS * 32, smem, stream>>>(sc, fp, d_out, pixelCounter, pp, reinterpret_cast<HitRecord*>(hits), hitCount, stats);
+    PoolQueue q = {nullptr, nullptr, 0u, 0u, 0u, nullptr};
+    k<<<grid, POOL_WARPS * 32, smem, stream>>>(sc, fp, d_out, pixelCounter, pp, reinterpret_cast<HitRecord*>(hits), hitCount, stats, q);
+    launches += 1;
+    return cudaGetLastError();
+}
+
+// Secondary rays from a queue of 48-byte records (rt_wavefront.cu): any-hit rays set occ[result] = 1 when blocked, closest-hit rays
+// append hit records tagged with their result index. `cursor` must be zero (the queue's read position).
+cudaError_t launch_rt_pool_queue(const DeviceScene& sc, const FrameParams& fp, bool anyhit, bool prune, const Switches& sw, unsigned* cursor,
+                                 const float4* rays, const unsigned* count, unsigned first, unsigned cap, unsigned stride,
+                                 unsigned char* occ, void* hits, unsigned* hitCount, int numSMs, cudaStream_t stream, int& launches)
+{
+    PoolParams pp;
+    memset(&pp, 0, sizeof pp);
+    fill_thresholds(pp, sw, prune);
+    size_t smem; int ctas;
+    PoolKernel k = anyhit ? pick_kernel<POOL_ANYHIT>(sw, false, smem, ctas) : pick_kernel<POOL_CLOSEST>(sw, false, smem, ctas);
+    PoolQueue q = {rays, count, first, cap, stride, occ};
+    k<<<numSMs * ctas, POOL_WARPS * 32, smem, stream>>>(sc, fp, nullptr, cursor, pp, reinterpret_cast<HitRecord*>(hits), hitCount, nullptr, q);
     launches += 1;
     return cudaGetLastError();
 }

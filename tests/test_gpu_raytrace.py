@@ -150,6 +150,9 @@ def test_pool_overflow_guard_and_legacy_pipeline_agree(rb, pyport, load_scene, g
         with gpu.switch("rt_legacy"):
             legacy = gpu.render(f)
         assert np.array_equal(legacy, pool), f"{model} frame {k} flags={flags}: job pipeline"
+        with gpu.switch("no_wavefront"):
+            threads = gpu.render(f)
+        assert np.array_equal(threads, pool), f"{model} frame {k} flags={flags}: rt_shade_kernel instead of the wavefront"
         if k == 3 and size[0] <= 1280:
             assert_parity(pool, pyport.render(s, f), f"{model} {size} frame {k} flags={flags}")
 
@@ -165,14 +168,15 @@ def test_pool_scheduling_variants_change_nothing(rb, load_scene, gpu, model, siz
     for flags in (1 | 4, 1 | 2 | 4):
         f = rb.make_frame(rb.MODE_RAYTRACE, size[0], size[1], cam, flags=flags)
         base = gpu.render(f)
-        for scatter_off in (0, 1):
+        for scatter in (1, 2):
             for policy in (0, 1, 2, 3):
-                gpu.set_switch("pool_no_scatter", scatter_off); gpu.set_switch("pool_policy", policy)
-                try:
-                    got = gpu.render(f)
-                finally:
-                    gpu.set_switch("pool_no_scatter", 0); gpu.set_switch("pool_policy", 0)
-                assert np.array_equal(got, base), f"{model} flags={flags} no_scatter={scatter_off} policy={policy}"
+                for occ3 in (0, 1):
+                    gpu.set_switch("pool_scatter", scatter); gpu.set_switch("pool_policy", policy); gpu.set_switch("pool_occ3", occ3)
+                    try:
+                        got = gpu.render(f)
+                    finally:
+                        gpu.set_switch("pool_scatter", 0); gpu.set_switch("pool_policy", 0); gpu.set_switch("pool_occ3", 0)
+                    assert np.array_equal(got, base), f"{model} flags={flags} scatter={scatter} policy={policy} occ3={occ3}"
 
 
 @pytest.mark.parametrize("model", ["chessboard.tri", "dragon_vis.ply", "trainColor.tri"])
@@ -245,32 +249,35 @@ def test_overlapped_async_frames_equal_blocking_frames(rb, load_scene, gpu):
 
 
 def test_frames_in_flight_on_scratch_slots_equal_blocking_frames(rb, load_scene, gpu):
-    """b200r_render_device_slot + renderer_b200.dist.FramePipeline (world 1): frames rotating over 4 streams / scratch sets,
-    and b200r_render_async at pipeline depth 4, deliver the blocking call's frames bit for bit."""
+    """b200r_pipeline (world 1): frames rotating over 4 streams / scratch sets, generic (AO + reflections, the wavefront) and
+    C2-type frames, and b200r_render_async at pipeline depth 4, deliver the blocking call's frames bit for bit."""
     import numpy as np
     import torch
-    from renderer_b200.dist import FramePipeline
     s = load_scene("chessboard.tri")
     gpu.upload(s)
     W, H, n = 1280, 720, 8
     cams = rb.Orbit.cameras(range(n))
-    frames = [rb.make_frame(rb.MODE_RAYTRACE, W, H, cams[k], flags=1 | 4, frame_index=k) for k in range(n)]
+    frames = [rb.make_frame(rb.MODE_RAYTRACE, W, H, cams[k], flags=(1 | 4) if k % 2 == 0 else (1 | 2 | 4 | 8), ao_samples=8, frame_index=k)
+              for k in range(n)]
     want = [gpu.render(f).copy() for f in frames]
-    pipe = FramePipeline(gpu, W, H, depth=4, to_host=True)
-    for base in (0, 4):
-        slots = [pipe.submit(frames[base + k]) for k in range(4)]
-        pipe.drain()
-        for k, d in enumerate(slots):
-            got = pipe.host[d].numpy().view(np.uint32)
-            assert np.array_equal(got, want[base + k]), f"pipeline frame {base + k}"
-            assert np.array_equal(pipe.full[d].cpu().numpy().view(np.uint32), want[base + k])
-    # a slot out of range / a rasteriser mode are refused, not rendered
-    import pytest
-    st = torch.cuda.Stream()
-    with pytest.raises(Exception):
-        gpu.render_device_slot(frames[0], pipe.full[0].data_ptr(), st.cuda_stream, 8)
-    with pytest.raises(Exception):
-        gpu.render_device_slot(rb.make_frame(rb.MODE_PHONG, W, H, cams[0]), pipe.full[0].data_ptr(), st.cuda_stream, 0)
+    pipe = rb.Pipeline(gpu, W, H, depth=4)
+    try:
+        hosts = [torch.zeros((H, W), dtype=torch.int32).pin_memory() for _ in range(n)]
+        for base in (0, 4):
+            for k in range(4):
+                pipe.submit(frames[base + k], hosts[base + k].data_ptr())
+            pipe.drain()
+            for k in range(4):
+                assert np.array_equal(hosts[base + k].numpy().view(np.uint32), want[base + k]), f"pipeline frame {base + k}"
+        # a slot out of range / the wireframe mode are refused, not rendered
+        import pytest
+        st = torch.cuda.Stream()
+        with pytest.raises(Exception):
+            gpu.render_device_slot(frames[0], pipe.slot_frame(0), st.cuda_stream, 8)
+        with pytest.raises(Exception):
+            gpu.render_device_slot(rb.make_frame(rb.MODE_LINES, W, H, cams[0]), pipe.slot_frame(0), st.cuda_stream, 0)
+    finally:
+        pipe.close()
     gpu.set_pipeline_depth(4)
     pinned = [torch.zeros((H, W), dtype=torch.int32).pin_memory() for _ in range(n)]
     outs = [p.numpy().view(np.uint32) for p in pinned]
