@@ -454,8 +454,14 @@ def run_b200_arm(args, wl):
     if True:
         pipe = rb.Pipeline(gpu, W, H, depth=depth, rank=rank, world=P, unique_id=job_id(), assemble=assemble)
         if do_flush:
-            pipe.set_l2_flush(FLUSH_BYTES, prefetch_scene=os.environ.get("B200R_BENCH_PREFETCH", "1") != "0")
+            # (a bulk L2 prefetch of the scene behind the flush - b200r_pipeline_set_prefetch - was measured and LOSES: one rank of 8
+            # emulated on one GPU 10 080 fps with it, 11 220 without; B200R_BENCH_PREFETCH=1 switches it on)
+            pipe.set_l2_flush(FLUSH_BYTES, prefetch_scene=os.environ.get("B200R_BENCH_PREFETCH", "0") == "1")
         frames = [frame_for(s_) for s_ in range(Wm + K)]         # frame state prepared outside the timed region (12 floats each)
+        fake = int(os.environ.get("B200R_BENCH_FAKE_SHARD", "0"))   # developer experiment: one GPU renders rows 0, P, 2P.. only (a rank's load)
+        if fake > 1 and P == 1:
+            for f_ in frames:
+                f_.row_first, f_.row_step = 0, fake
         for s_ in range(Wm):
             pipe.submit(frames[s_])
         pipe.drain()
@@ -533,6 +539,7 @@ def run_b200_arm(args, wl):
                               ("NOT flushed (B200R_BENCH_FLUSH=0: experiment, not a bench value)" if pipe_ms_per_step is not None else
                                "flushed between timed steps (144 MiB write, outside the events)")),
                        "frames_in_flight": in_flight,
+                       **({"EXPERIMENT_fake_shard": int(os.environ["B200R_BENCH_FAKE_SHARD"])} if os.environ.get("B200R_BENCH_FAKE_SHARD") else {}),
                        "host_enqueue_ms_per_step": enqueue_ms_per_step,
                        "parallelism": "1 GPU" if P == 1 else
                                       (f"row-cyclic sharding over {P} GPUs; rows assembled on every rank by " +

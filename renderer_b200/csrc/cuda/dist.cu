@@ -336,7 +336,7 @@ int b200r_pipeline_submit(b200r_pipeline* pipe, const b200r_frame* f, uint32_t* 
     const unsigned gen = (unsigned)(i / pipe->D);
     cudaStream_t rs = pipe->rs[d];
     b200r_frame fr = *f;
-    fr.row_first = P > 1 ? pipe->rank : 0; fr.row_step = P > 1 ? P : 1;
+    if (P > 1) { fr.row_first = pipe->rank; fr.row_step = P; }      // (world 1: the caller's own row selection is kept - experiments)
     const bool mlaa = (fr.flags & B200R_F_MLAA) != 0;
     fr.flags &= ~(uint32_t)B200R_F_MLAA;                         // the filter needs neighbouring rows: it runs on the assembled frame
     // ---- render stream of the slot: the slot's previous frame must have left the buffers this frame writes

@@ -276,6 +276,8 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
                     const float4 rl = P.rl[slot];
                     const bool occ = intersect_leaf(sc, mkv3(ro.x, ro.y, ro.z), mkv3(rd.x, rd.y, rd.z), it.x & ITEM_INDEX_MASK,
                                                     avoid, anyhit, mkv3(rl.x, rl.y, rl.z), best, bestK);
+                    // (another lane may be reading this slot's slack in the same pass: either value is right for it - it then
+                    // tests a leaf of a ray that is already decided - so this store needs no ordering; racecheck reports it as a hazard)
                     if (occ) P.ro[slot].w = -INF;
                     else if (bestK < k0) atomicMin(&P.key[slot], bestK);
                 }
@@ -309,6 +311,7 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
             freeMask |= __reduce_or_sync(FULL, freed ? (1u << slot) : 0u);
             shadeMask |= __reduce_or_sync(FULL, hit ? (1u << slot) : 0u);
             doneMask = 0u;
+            __syncwarp();               // the slots read here are re-armed / refilled by other lanes in the next pass
             continue;
         }
         // ------------------------------------------------------------------ resolved hits: shade + shadow ray / hit record
@@ -514,6 +517,7 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
             } else if (STATS) st_drop++;
             if (delta != 0) fin = (atomicAdd(&P.pend[slot], delta) + delta) == 0;
         }
+        __syncwarp();                   // every lane has read its entry before the pushes below reuse the popped part of the pool
         {
             const bool oneStack = policy == 1 || policy == 3;
             const bool hN = pN && !(cN & REF_LEAF), hF = pF && !(cF & REF_LEAF);      // inner children: near -> hot, far -> cold
@@ -647,11 +651,10 @@ cudaError_t launch_rt_pool(const DeviceScene& sc, const FrameParams& fp, uint32_
     size_t smem; int ctas;
     PoolKernel k = fused ? pick_kernel<POOL_FUSED>(sw, stats != nullptr, smem, ctas) : pick_kernel<POOL_PRIMARY>(sw, stats != nullptr, smem, ctas);
     int grid = numSMs * ctas;
-    // Grid: one tile per warp is the least a warp can take, and a frame rendered alone is latency-bound - every warp that can take rays
-    // shortens it (a rank's 1/8 of C2's rows, kernel alone: 1 tile per warp 0.146 ms, 4: 0.235, 16: 0.69). A rank of a many-GPU job
-    // keeps several frames in flight instead: 4 tiles per warp leave room for the kernels of 3 frames on every SM (8 x B200, 4 frames
-    // in flight per rank: 8263 fps).
-    const int tpw = sw.pool_tiles_per_warp > 0 ? sw.pool_tiles_per_warp : (fp.row_step >= 4 ? 4 : 1);
+    // Grid: one 8x4 tile per warp is the least a warp can take - and the best: a frame (or a rank's row shard of it) is latency-bound,
+    // every warp that can take rays shortens it. One rank of 8 emulated on one GPU (every 8th row of C2, 4 frames in flight, L2 flush per
+    // frame): 1 tile per warp 12 970 fps, 2: 12 280, 4: 10 080, 8: 7 560; kernel alone 0.146 / - / 0.235 / - ms.
+    const int tpw = sw.pool_tiles_per_warp > 0 ? sw.pool_tiles_per_warp : 1;
     const int needed = (pp.tiles.z * pp.tiles.w + POOL_WARPS * tpw - 1) / (POOL_WARPS * tpw);
     if (grid > needed) grid = needed;
     PoolQueue q = {nullptr, nullptr, 0u, 0u, 0u, nullptr};
