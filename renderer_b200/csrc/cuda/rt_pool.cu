@@ -261,7 +261,7 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
             const int n = min(32, lcount);
             lcount -= n;
             if (STATS) { st_it[1]++; st_ln[1] += n; }
-            bool fin = false; uint32_t slot = 0;
+            bool fin = false, occluded = false; uint32_t slot = 0;
             if ((int)lane < n) {
                 const uint2 it = P.lpool[lcount + n - 1 - (int)lane];
                 slot = (it.x >> ITEM_SLOT_SHIFT) & 31u;
@@ -276,13 +276,13 @@ rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsig
                     const float4 rl = P.rl[slot];
                     const bool occ = intersect_leaf(sc, mkv3(ro.x, ro.y, ro.z), mkv3(rd.x, rd.y, rd.z), it.x & ITEM_INDEX_MASK,
                                                     avoid, anyhit, mkv3(rl.x, rl.y, rl.z), best, bestK);
-                    // (another lane may be reading this slot's slack in the same pass: either value is right for it - it then
-                    // tests a leaf of a ray that is already decided - so this store needs no ordering; racecheck reports it as a hazard)
-                    if (occ) P.ro[slot].w = -INF;
-                    else if (bestK < k0) atomicMin(&P.key[slot], bestK);
+                    occluded = occ;
+                    if (!occ && bestK < k0) atomicMin(&P.key[slot], bestK);
                 }
                 fin = atomicSub(&P.pend[slot], 1) == 1;
             }
+            __syncwarp();               // every lane has read its slot's state: now the occlusion marks may be written
+            if (occluded) P.ro[slot].w = -INF;
             doneMask |= __reduce_or_sync(FULL, fin ? (1u << slot) : 0u);
             __syncwarp();
             continue;
