@@ -40,13 +40,15 @@ WORKLOADS = {
 }
 
 
-# ray-traced frames in flight (bench protocol "pipelined" and the e2e leg); B200R_BENCH_DEPTH / B200R_E2E_DEPTH override.
-# Measured on one B200 (profiles/README.md, session r01i): 2 frames in flight 3620 fps, 3: 3370, 4: 3290, 6: 2990 - on one GPU a
-# third frame only adds contention; with the frame's rows dealt over N GPUs each rank's kernel is short and latency-bound, so
-# more frames are needed to fill it.
-# r01i, one GPU rendering every 2nd / 8th row only (what a rank of 2 / 8 does): 4 in flight 4940 / 15700 fps, 8 in flight 6700 (8th rows).
-DEFAULT_DEPTH = 2
-DEFAULT_DEPTH_SHARDED = 4
+# frames in flight (bench protocol "pipelined" and the e2e leg); B200R_BENCH_DEPTH / B200R_E2E_DEPTH override.
+# Measured on one B200 with rt_pool_kernel (profiles/README.md, sessions r03b-e; every slot warmed before the timed region - the
+# earlier "6 or 8 in flight lose" was the first-use cudaMalloc of slots 4.. inside it): C2, 4-warp CTAs: 2 in flight 3950 fps,
+# 3: 4410, 4-8: 4510-4550. With the frame's rows dealt over N GPUs each rank's launch is short and latency-bound, so more frames
+# are needed to fill the GPU: one rank of 8 emulated (every 8th row) 2 in flight 10 100 fps, 4: 13 800, 6: 15 300, 8: 15 400.
+# e2e (8.3 MB per frame out over PCIe, a slot is busy until its frame has left): 2 slots 3250 fps, 3: 4530, 4: 4770-4980.
+DEFAULT_DEPTH = 4
+DEFAULT_DEPTH_SHARDED = 6
+DEFAULT_E2E_DEPTH = 4
 FLUSH_BYTES = 144 << 20      # > 126 MB L2
 
 
@@ -462,8 +464,8 @@ def run_b200_arm(args, wl):
         if fake > 1 and P == 1:
             for f_ in frames:
                 f_.row_first, f_.row_step = 0, fake
-        for s_ in range(Wm):
-            pipe.submit(frames[s_])
+        for s_ in range(max(Wm, 2 * depth)):          # every slot allocates its scratch buffers on first use: warm all of them
+            pipe.submit(frames[s_ % Wm])
         pipe.drain()
         barrier()
         pipe.launches(reset=True)
@@ -495,16 +497,20 @@ def run_b200_arm(args, wl):
             clocks = clocks2
         # ---- end to end through the same public call with HOST buffers: every assembled frame is copied to page-locked host memory
         # of rank 0 (N = 1: of the one rank) inside the timed region; no L2 flush here (the user-facing call has none)
-        pipe.set_l2_flush(0)
-        e2e_depth = int(os.environ.get("B200R_E2E_DEPTH", "0")) or depth
-        hosts = [torch.zeros((H, W), dtype=torch.int32).pin_memory() for _ in range(depth)] if rank == 0 else None
-        for s_ in range(min(Wm, 3)):
-            pipe.submit(frames[s_], hosts[s_ % depth].data_ptr() if hosts else None)
+        # (its own pipeline: a slot is busy until its frame has left over PCIe - 8.3 MB, ~0.17 ms at 1080p - so the copy-out wants one
+        # more slot than the device-only protocol)
+        barrier()
+        pipe.close()
+        e2e_depth = int(os.environ.get("B200R_E2E_DEPTH", "0")) or (DEFAULT_E2E_DEPTH if P == 1 else depth)
+        pipe = rb.Pipeline(gpu, W, H, depth=e2e_depth, rank=rank, world=P, unique_id=job_id(), assemble=assemble)
+        hosts = [torch.zeros((H, W), dtype=torch.int32).pin_memory() for _ in range(e2e_depth)] if rank == 0 else None
+        for s_ in range(max(Wm, 2 * e2e_depth)):
+            pipe.submit(frames[s_ % Wm], hosts[s_ % e2e_depth].data_ptr() if hosts else None)
         pipe.drain()
         barrier()
         t0 = time.perf_counter()
         for i in range(K):
-            pipe.submit(frames[Wm + i], hosts[i % depth].data_ptr() if hosts else None)
+            pipe.submit(frames[Wm + i], hosts[i % e2e_depth].data_ptr() if hosts else None)
         pipe.drain()                     # every frame of the timed region is complete in rank 0's host memory
         barrier()
         e2e_s = time.perf_counter() - t0

@@ -262,7 +262,7 @@ int  b200r_get_tile_profile(b200r_ctx* ctx, uint64_t* start_end_ns, uint32_t max
 
 /* Developer switches: select cross-check variants of the kernels (parity tests, A/B measurements); none changes a result.
  * Names: monolithic_rt, no_prune, no_fuse, no_wavefront, rt_legacy, no_root_rect, pool_small, split_depth, raster_inline_shade, mlaa_scan,
- * mlaa_fullscan, mlaa_nobatch, mlaa_no_tma, no_frame_overlap, bvh_serial_split, pool_stats, pool_policy, pool_scatter, pool_occ3, pool_tiles_per_warp,
+ * mlaa_fullscan, mlaa_nobatch, mlaa_no_tma, no_frame_overlap, bvh_serial_split, pool_stats, pool_policy, pool_scatter, pool_occ3, pool_tiles_per_warp, pool_cta_warps,
  * pool_leaf_min, pool_sort_min, pool_shade_min, pool_refill_min, pool_low_water, pool_dry (csrc/cuda/rt_kernels.cuh `Switches` documents each).
  * Defaults come from the environment variables B200R_<NAME IN CAPITALS>, read once by b200r_init. Waits for frames in flight. */
 int  b200r_set_switch(b200r_ctx* ctx, const char* name, int value);

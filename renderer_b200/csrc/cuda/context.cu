@@ -391,7 +391,7 @@ const SwitchName kSwitches[] = {
     {"split_depth", &Switches::split_depth}, {"raster_inline_shade", &Switches::raster_inline_shade}, {"mlaa_scan", &Switches::mlaa_scan},
     {"mlaa_fullscan", &Switches::mlaa_fullscan}, {"mlaa_nobatch", &Switches::mlaa_nobatch}, {"mlaa_no_tma", &Switches::mlaa_no_tma},
     {"no_frame_overlap", &Switches::no_frame_overlap}, {"bvh_serial_split", &Switches::bvh_serial_split},
-    {"pool_stats", &Switches::pool_stats}, {"pool_policy", &Switches::pool_policy}, {"pool_scatter", &Switches::pool_scatter}, {"pool_occ3", &Switches::pool_occ3}, {"pool_tiles_per_warp", &Switches::pool_tiles_per_warp},
+    {"pool_stats", &Switches::pool_stats}, {"pool_policy", &Switches::pool_policy}, {"pool_scatter", &Switches::pool_scatter}, {"pool_occ3", &Switches::pool_occ3}, {"pool_tiles_per_warp", &Switches::pool_tiles_per_warp}, {"pool_cta_warps", &Switches::pool_cta_warps},
     {"pool_leaf_min", &Switches::pool_leaf_min}, {"pool_sort_min", &Switches::pool_sort_min}, {"pool_shade_min", &Switches::pool_shade_min},
     {"pool_refill_min", &Switches::pool_refill_min}, {"pool_low_water", &Switches::pool_low_water}, {"pool_dry", &Switches::pool_dry},
 };

@@ -38,7 +38,7 @@ using namespace rt;
 
 namespace {
 
-constexpr int POOL_WARPS = 8;            // warps per CTA (independent of each other)
+constexpr int POOL_WARPS = 8;            // most warps per CTA (independent of each other); the default is 4 - pool_cta_warps = 8 / 2 / 1: as many warps per SM
 constexpr int POOL_CTAS_PER_SM = 3;
 constexpr int CAP_L = 128;               // leaf pool: < LEAF_MIN waiting + at most 64 pushed per inner iteration (+ 32 roots)
 // scheduling thresholds (defaults; developer switches pool_* override them for tuning)
@@ -223,8 +223,8 @@ struct PoolQueue {
 };
 
 // STATS (developer switch pool_stats): per-phase iteration / lane counts are added to DeviceCounters (tools/pool_stats.py).
-template <int MODE, int CAP_I, bool STATS = false, int CTAS = POOL_CTAS_PER_SM>
-__global__ void __launch_bounds__(POOL_WARPS * 32, CTAS)
+template <int MODE, int CAP_I, bool STATS = false, int CTAS = POOL_CTAS_PER_SM, int WARPS = POOL_WARPS>
+__global__ void __launch_bounds__(WARPS * 32, CTAS * (POOL_WARPS / WARPS))
 rt_pool_kernel(DeviceScene sc, FrameParams fp, uint32_t* __restrict__ out, unsigned* __restrict__ pixelCounter, PoolParams pp,
                HitRecord* __restrict__ hits, unsigned* __restrict__ hitCount, DeviceCounters* __restrict__ stats, PoolQueue q)
 {
@@ -578,17 +578,31 @@ bool pool_supported(const DeviceScene& sc)
 namespace {
 using PoolKernel = void (*)(DeviceScene, FrameParams, uint32_t*, unsigned*, PoolParams, HitRecord*, unsigned*, DeviceCounters*, PoolQueue);
 
+// `warps` = warps per CTA of the kernel picked, `ctas` = CTAs of that size per SM (always 24 or 32 warps per SM). Warps never
+// synchronise with each other, so the CTA size only decides how soon a finished warp's share of the SM goes to a waiting CTA
+// - of the NEXT frame in flight: a CTA leaves when its slowest warp does.
 template <int MODE>
-PoolKernel pick_kernel(const Switches& sw, bool stats, size_t& smem, int& ctas)
+PoolKernel pick_kernel(const Switches& sw, bool stats, size_t& smem, int& ctas, int& warps)
 {
-    ctas = POOL_CTAS_PER_SM;
+    ctas = POOL_CTAS_PER_SM; warps = POOL_WARPS;
     if (sw.pool_small) { smem = sizeof(WarpPool<128>) * POOL_WARPS; return rt_pool_kernel<MODE, 128>; }
     smem = sizeof(WarpPool<512>) * POOL_WARPS;
     if (stats && MODE <= POOL_PRIMARY) return rt_pool_kernel<(MODE <= POOL_PRIMARY ? MODE : 0), 512, true>;
+    // Measured on one B200 (C2, frames in flight, L2 flush per frame; profiles/README.md sessions r03b-e): 3 in flight 8 warps 4287 fps,
+    // 4 warps 4411, 2 warps 4409; 6 in flight 4386 / 4510 / 4538; alone 0.3205 / 0.3200 / 0.327 ms (1 warp: 0.341); one rank of 8
+    // emulated, 8 in flight: 15 264 / 15 438 / 15 118 fps. Default: 4 warps per CTA.
+    int w = sw.pool_cta_warps == 8 || sw.pool_cta_warps == 2 || sw.pool_cta_warps == 1 ? sw.pool_cta_warps : 4;
+    if (w == 1 && (MODE != POOL_FUSED || sw.pool_occ3)) w = 2;        // one-warp CTAs (32 per SM) exist for the C2-type kernel only
     if (!sw.pool_occ3 && MODE == POOL_FUSED) {          // C2-type frames: 4 CTAs per SM (64 registers per thread, 256-entry pools): 0.339 ms vs 0.355 with 3
-        smem = sizeof(WarpPool<256>) * POOL_WARPS; ctas = 4;
+        smem = sizeof(WarpPool<256>) * w; ctas = 4 * (POOL_WARPS / w); warps = w;
+        if (w == 4) return rt_pool_kernel<POOL_FUSED, 256, false, 4, 4>;
+        if (w == 2) return rt_pool_kernel<POOL_FUSED, 256, false, 4, 2>;
+        if (w == 1) return rt_pool_kernel<POOL_FUSED, 256, false, 4, 1>;
         return rt_pool_kernel<POOL_FUSED, 256, false, 4>;
     }
+    smem = sizeof(WarpPool<512>) * w; ctas = POOL_CTAS_PER_SM * (POOL_WARPS / w); warps = w;
+    if (w == 4) return rt_pool_kernel<MODE, 512, false, POOL_CTAS_PER_SM, 4>;
+    if (w == 2) return rt_pool_kernel<MODE, 512, false, POOL_CTAS_PER_SM, 2>;
     return rt_pool_kernel<MODE, 512>;
 }
 
@@ -616,6 +630,12 @@ cudaError_t rt_pool_configure()
     set(rt_pool_kernel<POOL_FUSED, 128>, small); set(rt_pool_kernel<POOL_PRIMARY, 128>, small);
     set(rt_pool_kernel<POOL_ANYHIT, 128>, small); set(rt_pool_kernel<POOL_CLOSEST, 128>, small);
     set(rt_pool_kernel<POOL_FUSED, 256, false, 4>, mid);
+    set(rt_pool_kernel<POOL_FUSED, 256, false, 4, 4>, mid / 2); set(rt_pool_kernel<POOL_FUSED, 256, false, 4, 2>, mid / 4);
+    set(rt_pool_kernel<POOL_FUSED, 256, false, 4, 1>, mid / 8);
+    set(rt_pool_kernel<POOL_FUSED, 512, false, POOL_CTAS_PER_SM, 4>, big / 2); set(rt_pool_kernel<POOL_FUSED, 512, false, POOL_CTAS_PER_SM, 2>, big / 4);
+    set(rt_pool_kernel<POOL_PRIMARY, 512, false, POOL_CTAS_PER_SM, 4>, big / 2); set(rt_pool_kernel<POOL_PRIMARY, 512, false, POOL_CTAS_PER_SM, 2>, big / 4);
+    set(rt_pool_kernel<POOL_ANYHIT, 512, false, POOL_CTAS_PER_SM, 4>, big / 2); set(rt_pool_kernel<POOL_ANYHIT, 512, false, POOL_CTAS_PER_SM, 2>, big / 4);
+    set(rt_pool_kernel<POOL_CLOSEST, 512, false, POOL_CTAS_PER_SM, 4>, big / 2); set(rt_pool_kernel<POOL_CLOSEST, 512, false, POOL_CTAS_PER_SM, 2>, big / 4);
     return e;
 }
 
@@ -648,17 +668,17 @@ cudaError_t launch_rt_pool(const DeviceScene& sc, const FrameParams& fp, uint32_
         pp.scatterMul = m % pp.nGroups;
         pp.scatterInv = ~0ull / pp.nGroups;
     }
-    size_t smem; int ctas;
-    PoolKernel k = fused ? pick_kernel<POOL_FUSED>(sw, stats != nullptr, smem, ctas) : pick_kernel<POOL_PRIMARY>(sw, stats != nullptr, smem, ctas);
+    size_t smem; int ctas, warps;
+    PoolKernel k = fused ? pick_kernel<POOL_FUSED>(sw, stats != nullptr, smem, ctas, warps) : pick_kernel<POOL_PRIMARY>(sw, stats != nullptr, smem, ctas, warps);
     int grid = numSMs * ctas;
     // Grid: one 8x4 tile per warp is the least a warp can take - and the best: a frame (or a rank's row shard of it) is latency-bound,
     // every warp that can take rays shortens it. One rank of 8 emulated on one GPU (every 8th row of C2, 4 frames in flight, L2 flush per
     // frame): 1 tile per warp 12 970 fps, 2: 12 280, 4: 10 080, 8: 7 560; kernel alone 0.146 / - / 0.235 / - ms.
     const int tpw = sw.pool_tiles_per_warp > 0 ? sw.pool_tiles_per_warp : 1;
-    const int needed = (pp.tiles.z * pp.tiles.w + POOL_WARPS * tpw - 1) / (POOL_WARPS * tpw);
+    const int needed = (pp.tiles.z * pp.tiles.w + warps * tpw - 1) / (warps * tpw);
     if (grid > needed) grid = needed;
     PoolQueue q = {nullptr, nullptr, 0u, 0u, 0u, nullptr};
-    k<<<grid, POOL_WARPS * 32, smem, stream>>>(sc, fp, d_out, pixelCounter, pp, reinterpret_cast<HitRecord*>(hits), hitCount, stats, q);
+    k<<<grid, warps * 32, smem, stream>>>(sc, fp, d_out, pixelCounter, pp, reinterpret_cast<HitRecord*>(hits), hitCount, stats, q);
     launches += 1;
     return cudaGetLastError();
 }
@@ -672,10 +692,10 @@ cudaError_t launch_rt_pool_queue(const DeviceScene& sc, const FrameParams& fp, b
     PoolParams pp;
     memset(&pp, 0, sizeof pp);
     fill_thresholds(pp, sw, prune);
-    size_t smem; int ctas;
-    PoolKernel k = anyhit ? pick_kernel<POOL_ANYHIT>(sw, false, smem, ctas) : pick_kernel<POOL_CLOSEST>(sw, false, smem, ctas);
+    size_t smem; int ctas, warps;
+    PoolKernel k = anyhit ? pick_kernel<POOL_ANYHIT>(sw, false, smem, ctas, warps) : pick_kernel<POOL_CLOSEST>(sw, false, smem, ctas, warps);
     PoolQueue q = {rays, count, first, cap, stride, occ};
-    k<<<numSMs * ctas, POOL_WARPS * 32, smem, stream>>>(sc, fp, nullptr, cursor, pp, reinterpret_cast<HitRecord*>(hits), hitCount, nullptr, q);
+    k<<<numSMs * ctas, warps * 32, smem, stream>>>(sc, fp, nullptr, cursor, pp, reinterpret_cast<HitRecord*>(hits), hitCount, nullptr, q);
     launches += 1;
     return cudaGetLastError();
 }

@@ -177,6 +177,22 @@ def test_pool_scheduling_variants_change_nothing(rb, load_scene, gpu, model, siz
                     finally:
                         gpu.set_switch("pool_scatter", 0); gpu.set_switch("pool_policy", 0); gpu.set_switch("pool_occ3", 0)
                     assert np.array_equal(got, base), f"{model} flags={flags} scatter={scatter} policy={policy} occ3={occ3}"
+        # CTA size (default 4 independent warps per CTA; 8, 2, 1: the same number of warps per SM): scheduling only, too
+        for warps in (8, 2, 1):
+            for scatter in (1, 2):
+                gpu.set_switch("pool_cta_warps", warps); gpu.set_switch("pool_scatter", scatter)
+                try:
+                    got = gpu.render(f)
+                finally:
+                    gpu.set_switch("pool_cta_warps", 0); gpu.set_switch("pool_scatter", 0)
+                assert np.array_equal(got, base), f"{model} flags={flags} cta_warps={warps} scatter={scatter}"
+    if size[0] <= 801:      # AO + reflections: the queue modes of the kernel with small CTAs
+        f = rb.make_frame(rb.MODE_RAYTRACE, size[0], size[1], cam, flags=1 | 2 | 4 | 8, ao_samples=4)
+        base = gpu.render(f)
+        for warps in (8, 2):
+            with gpu.switch("pool_cta_warps", warps):
+                got = gpu.render(f)
+            assert np.array_equal(got, base), f"{model} AO cta_warps={warps}"
 
 
 @pytest.mark.parametrize("model", ["chessboard.tri", "dragon_vis.ply", "trainColor.tri"])
