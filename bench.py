@@ -44,10 +44,10 @@ WORKLOADS = {
 # Measured on one B200 with rt_pool_kernel (profiles/README.md, sessions r03b-e; every slot warmed before the timed region - the
 # earlier "6 or 8 in flight lose" was the first-use cudaMalloc of slots 4.. inside it): C2, 4-warp CTAs: 2 in flight 3950 fps,
 # 3: 4410, 4-8: 4510-4550. With the frame's rows dealt over N GPUs each rank's launch is short and latency-bound, so more frames
-# are needed to fill the GPU: one rank of 8 emulated (every 8th row) 2 in flight 10 100 fps, 4: 13 800, 6: 15 300, 8: 15 400.
+# are needed to fill the GPU: one rank of 8 emulated (every 8th row) 2 in flight 10 100 fps, 4: 13 800, 6: 16 070, 8: 17 320, 12: 17 770.
 # e2e (8.3 MB per frame out over PCIe, a slot is busy until its frame has left): 2 slots 3250 fps, 3: 4530, 4: 4770-4980.
 DEFAULT_DEPTH = 4
-DEFAULT_DEPTH_SHARDED = 6
+DEFAULT_DEPTH_SHARDED = 8
 DEFAULT_E2E_DEPTH = 4
 FLUSH_BYTES = 144 << 20      # > 126 MB L2
 
@@ -540,7 +540,7 @@ def run_b200_arm(args, wl):
             "config": {"workload": wl["desc"], "camera": "reference -b orbit, one new frame per step",
                        "rays_per_frame": rays_total / K,
                        "raster_per_frame": ({k: tot_all[k] / K for k in ("tris_setup", "spans", "z_tests", "z_passes")} if raster else None),
-                       "l2": ("flushed before every frame: a 144 MiB write (> 126 MB L2) enqueued on the frame's stream, INSIDE the timed region"
+                       "l2": ("flushed before every frame: a 144 MiB write (> 126 MB L2; 16-byte stores from two 128-thread CTAs per SM) enqueued on the frame's stream, INSIDE the timed region"
                               if pipe_ms_per_step is not None and do_flush else
                               ("NOT flushed (B200R_BENCH_FLUSH=0: experiment, not a bench value)" if pipe_ms_per_step is not None else
                                "flushed between timed steps (144 MiB write, outside the events)")),

@@ -38,7 +38,7 @@ extern "C" {
 #define B200R_BVH_STACK_SIZE 32     /* reference src/Defines.h:36 */
 #define B200R_SHADOWMAP_SIZE 1024   /* reference src/Defines.h:25 */
 #define B200R_MAX_LIGHTS     2      /* reference src/renderer.cc:277-296 (-w adds the second) */
-#define B200R_MAX_FRAMES_IN_FLIGHT 8 /* independent sets of per-frame scratch buffers (b200r_set_pipeline_depth, b200r_render_device_slot) */
+#define B200R_MAX_FRAMES_IN_FLIGHT 16 /* independent sets of per-frame scratch buffers (b200r_set_pipeline_depth, b200r_render_device_slot) */
 
 /* ---------------------------------------------------------------- scene records (POD)
  * These mirror the fields of the reference's Vertex / Triangle / CacheFriendlyBVHNode that the

@@ -137,6 +137,20 @@ __global__ void signal_peers_kernel(SignalArgs a, int P)
     if (threadIdx.x < (unsigned)P) atomicAdd_system(a.word[threadIdx.x], 1u);
 }
 
+// Measurement aid (b200r_pipeline_set_l2_flush): write a buffer larger than the L2 so that the frame behind it starts from a cold
+// cache. The same bytes as a cudaMemsetAsync of the buffer, but from two small CTAs per SM instead of the runtime's 73 728-CTA fill
+// kernel: the persistent render CTAs of the frames in flight own every register of an SM, so a fill grid of that size cannot run
+// beside them - it displaces them for the whole 23 us the write takes (measured on one rank of 8 emulated, 8 frames in flight:
+// 15 260 fps with cudaMemsetAsync, 23 370 fps without any flush) - while 16-byte stores from 256 threads per SM already saturate HBM.
+__global__ void __launch_bounds__(128) l2_flush_kernel(uint4* __restrict__ p, size_t n16)
+{
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    const size_t stride = (size_t)gridDim.x * 128;
+    size_t i = (size_t)blockIdx.x * 128 + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) { p[i] = z; p[i + stride] = z; p[i + 2 * stride] = z; p[i + 3 * stride] = z; }
+    for (; i < n16; i += stride) p[i] = z;
+}
+
 // prefetch a buffer into L2 (after a bench-mode L2 flush the scene would otherwise come back one 64-byte miss at a time)
 __global__ void l2_prefetch_kernel(const char* p, size_t bytes)
 {
@@ -168,6 +182,7 @@ struct b200r_pipeline {
     void* nccl = nullptr;
     uint64_t submitted = 0;
     void* flushBuf = nullptr; size_t flushBytes = 0;
+    bool flushMemset = false;                     // B200R_PIPE_FLUSH_MEMSET=1: the flush by cudaMemsetAsync (A/B)
     const char* prefetch[4] = {}; size_t prefetchBytes[4] = {};
     uint32_t launches = 0;
     bool timing = false;
@@ -334,6 +349,7 @@ int b200r_pipeline_set_l2_flush(b200r_pipeline* pipe, uint64_t bytes)
     PCU(cudaSetDevice(pipe->device));
     if (pipe->flushBuf) { cudaFree(pipe->flushBuf); pipe->flushBuf = nullptr; }
     pipe->flushBytes = (size_t)bytes;
+    pipe->flushMemset = getenv("B200R_PIPE_FLUSH_MEMSET") != nullptr;
     if (bytes) PCU(cudaMalloc(&pipe->flushBuf, (size_t)bytes));
     return B200R_OK;
 }
@@ -361,7 +377,8 @@ int b200r_pipeline_submit(b200r_pipeline* pipe, const b200r_frame* f, uint32_t* 
     // ---- render stream of the slot: the slot's previous frame must have left the buffers this frame writes
     if (i >= pipe->D) PCU(cudaStreamWaitEvent(rs, P > 1 ? pipe->pushed[d] : pipe->consumed[d], 0));
     if (pipe->flushBuf) {
-        PCU(cudaMemsetAsync(pipe->flushBuf, 0, pipe->flushBytes, rs));           // measurement aid: evict the L2 before the frame ...
+        if (pipe->flushMemset) PCU(cudaMemsetAsync(pipe->flushBuf, 0, pipe->flushBytes, rs));      // measurement aid: evict the L2 before the frame ...
+        else { l2_flush_kernel<<<pipe->sms * 2, 128, 0, rs>>>((uint4*)pipe->flushBuf, pipe->flushBytes / 16); PCU(cudaGetLastError()); pipe->launches += 1; }
         for (int k = 0; k < 4; k++)                                               // ... and pull the scene back in bulk, not miss by miss
             if (pipe->prefetch[k]) { l2_prefetch_kernel<<<pipe->sms, 256, 0, rs>>>(pipe->prefetch[k], pipe->prefetchBytes[k]); pipe->launches += 1; }
     }

@@ -24,7 +24,7 @@ struct Switches {
     int bvh_serial_split = 0;     // BVH build: one thread per node in every level
     int pool_policy = 0;          // rt_pool_kernel: how the inner pool is popped (rt_pool.cu PoolParams)
     int pool_leaf_min = 0, pool_sort_min = 0, pool_shade_min = 0, pool_refill_min = 0, pool_low_water = 0, pool_dry = 0;   // rt_pool_kernel thresholds (0 = built-in)
-    int pool_tiles_per_warp = 0;  // rt_pool_kernel: grid sized for this many 8x4 tiles per warp (0 = built-in 4)
+    int pool_tiles_per_warp = 0;  // rt_pool_kernel: grid sized for this many 8x4 tiles per warp (0 = built-in: 1 for a frame alone, 2 with frames in flight)
     int pool_cta_warps = 0;       // rt_pool_kernel: warps per CTA (0 = built-in 4; 8, 2, 1: the same number of warps per SM in larger / smaller CTAs)
     int pool_occ3 = 0;            // rt_pool_kernel: C2-type frames with 3 CTAs per SM (76 registers, 512-entry pools) instead of 4
     int pool_scatter = 0;         // rt_pool_kernel: 0 = scattered 4-pixel groups for a frame alone, whole 8x4 tiles for frames in flight; 1 / 2 force

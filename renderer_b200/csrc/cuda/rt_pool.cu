@@ -671,10 +671,12 @@ cudaError_t launch_rt_pool(const DeviceScene& sc, const FrameParams& fp, uint32_
     size_t smem; int ctas, warps;
     PoolKernel k = fused ? pick_kernel<POOL_FUSED>(sw, stats != nullptr, smem, ctas, warps) : pick_kernel<POOL_PRIMARY>(sw, stats != nullptr, smem, ctas, warps);
     int grid = numSMs * ctas;
-    // Grid: one 8x4 tile per warp is the least a warp can take - and the best: a frame (or a rank's row shard of it) is latency-bound,
-    // every warp that can take rays shortens it. One rank of 8 emulated on one GPU (every 8th row of C2, 4 frames in flight, L2 flush per
-    // frame): 1 tile per warp 12 970 fps, 2: 12 280, 4: 10 080, 8: 7 560; kernel alone 0.146 / - / 0.235 / - ms.
-    const int tpw = sw.pool_tiles_per_warp > 0 ? sw.pool_tiles_per_warp : 1;
+    // Grid: a frame rendered alone (or a rank's row shard of it) is latency-bound and every warp that can take rays shortens it: one 8x4
+    // tile per warp (kernel alone on every 8th row of C2: 0.146 ms with 1 tile per warp, 0.235 with 4). With frames IN FLIGHT the other
+    // frames hide that latency and fuller warps waste fewer lanes (a warp with its one tile's ~27 rays runs its inner passes at 16.6 of
+    // 32 lanes; a full frame's warps at 25.7): one rank of 8 emulated on one GPU, 8 frames in flight, L2 flush per frame:
+    // 1 tile per warp 15 260 fps, 2: 17 040, 4: 16 180 (12 in flight: 15 360 / 16 730 / -).
+    const int tpw = sw.pool_tiles_per_warp > 0 ? sw.pool_tiles_per_warp : (inFlight ? 2 : 1);
     const int needed = (pp.tiles.z * pp.tiles.w + warps * tpw - 1) / (warps * tpw);
     if (grid > needed) grid = needed;
     PoolQueue q = {nullptr, nullptr, 0u, 0u, 0u, nullptr};
