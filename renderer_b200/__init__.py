@@ -16,7 +16,7 @@ from . import _abi
 from ._abi import (F_AO, F_DEFAULT, F_MLAA, F_PHONG_NORMAL, F_REFLECTIONS, F_SHADOWS,  # noqa: F401
                    MODE_AMBIENT, MODE_GOURAUD, MODE_LINES, MODE_PHONG, MODE_PHONG_SHADOWMAPS,
                    MODE_PHONG_SOFTSHADOWMAPS, MODE_POINTS, MODE_POINTS_TRI, MODE_RAYTRACE,
-                   MODE_RAYTRACE_AA, Counters, Frame)
+                   MODE_RAYTRACE_AA, MAX_FRAMES_IN_FLIGHT, Counters, Frame)
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200R_LIB") or os.path.join(_PKG, "libb200render.so")   # (B200R_LIB: developer builds)

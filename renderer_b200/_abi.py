@@ -2,6 +2,7 @@
 import ctypes as C
 
 MAX_LIGHTS = 2
+MAX_FRAMES_IN_FLIGHT = 16      # B200R_MAX_FRAMES_IN_FLIGHT
 SHADOWMAP_SIZE = 1024
 
 F_SHADOWS, F_REFLECTIONS, F_PHONG_NORMAL, F_AO, F_MLAA = 0x01, 0x02, 0x04, 0x08, 0x10

@@ -33,15 +33,15 @@ def test_struct_sizes_match_c(rb):
     prog = r'''
 #include <stdio.h>
 #include "b200render.h"
-int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(b200r_vertex), sizeof(b200r_tri), sizeof(b200r_bvhnode),
-  sizeof(b200r_light), sizeof(b200r_frame), sizeof(b200r_counters), sizeof(b200r_orbit)); return 0; }'''
+int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %d\n", sizeof(b200r_vertex), sizeof(b200r_tri), sizeof(b200r_bvhnode),
+  sizeof(b200r_light), sizeof(b200r_frame), sizeof(b200r_counters), sizeof(b200r_orbit), B200R_MAX_FRAMES_IN_FLIGHT); return 0; }'''
     with tempfile.TemporaryDirectory() as td:
         c = os.path.join(td, "s.c"); open(c, "w").write(prog)
         exe = os.path.join(td, "s")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     want = [C.sizeof(t) for t in (_abi.Vertex, _abi.Tri, _abi.BvhNode, _abi.Light, _abi.Frame, _abi.Counters, _abi.Orbit)]
-    assert sizes == want
+    assert sizes[:-1] == want and sizes[-1] == _abi.MAX_FRAMES_IN_FLIGHT
     assert sizes[0] == 28 and sizes[2] == 32      # = reference Vertex / CacheFriendlyBVHNode
 
 

@@ -289,7 +289,7 @@ def test_frames_in_flight_on_scratch_slots_equal_blocking_frames(rb, load_scene,
         import pytest
         st = torch.cuda.Stream()
         with pytest.raises(Exception):
-            gpu.render_device_slot(frames[0], pipe.slot_frame(0), st.cuda_stream, 8)
+            gpu.render_device_slot(frames[0], pipe.slot_frame(0), st.cuda_stream, rb.MAX_FRAMES_IN_FLIGHT)
         with pytest.raises(Exception):
             gpu.render_device_slot(rb.make_frame(rb.MODE_LINES, W, H, cams[0]), pipe.slot_frame(0), st.cuda_stream, 0)
     finally:
