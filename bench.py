@@ -21,6 +21,11 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# One hardware work queue per stream of the frame pipeline (up to 8 render streams + push + consume + the timing stream): the
+# CUDA default of 8 connections would let streams share a queue, and a rank's arrival-wait kernel could then hold back the next
+# frame's render kernel queued behind it (false dependency; never a deadlock - every dependency points to earlier-submitted work).
+# Must be set before CUDA is initialised; measured on one GPU: no effect on the numbers (session r03d).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 WORKLOADS = {
     # name: model, W, H, mode, flags (1 shadows, 2 reflections, 4 phong normal, 8 AO), ao samples, ref-variant kwargs

@@ -65,6 +65,7 @@ static double now_ms()
 
 int main(int argc, char* argv[])
 {
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);      // one hardware queue per stream of the frame pipeline (before CUDA starts)
     unsigned mode = B200R_MODE_PHONG_SOFTSHADOWMAPS;     // reference default (renderer.cc:177)
     bool doReports = false, doBenchmark = false, useTwoLights = false;
     unsigned benchmarkFrames = 100;

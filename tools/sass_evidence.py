@@ -65,15 +65,15 @@ def report(path, title, obj, log, needle, want, excerpt=None):
 
 
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-report(os.path.join(ROOT, "profiles", "r02_sass_rt_pool_kernel.txt"),
+report(os.path.join(ROOT, "profiles", "r03_sass_rt_pool_kernel.txt"),
        "rt_pool_kernel (all instantiations). walk_subtree (__noinline__, the cold overflow path) is emitted behind the kernel body: its private\n"
        "# DFS stack is the local memory at the high addresses; the 64-register instantiation (4 CTAs per SM) additionally spills 24 bytes;\n"
        "# node records (4 x LDG.E.128) and leaf records (5 x LDG.E.128) are fetched with 128-bit loads, slot state with LDS.128, pool entries with LDS.64/STS.64",
        os.path.join(B, "rt_pool.cu.o"), os.path.join(B, "rt_pool.cu.o.log"), "rt_pool",
        ("LDG", "LDS", "STS", "ATOMS", "VOTE", "REDUX", "LDL", "STL", "FFMA", "FMNMX", "CALL", "WARPSYNC", "STG"), r"LDG\.E\.128|ATOMS|REDUX")
-report(os.path.join(ROOT, "profiles", "r02_sass_mlaa_tma.txt"),
+report(os.path.join(ROOT, "profiles", "r03_sass_mlaa_tma.txt"),
        "mlaa_blend_vstrip_tma_kernel: the strip is loaded with UTMALDG.2D (cp.async.bulk.tensor.2d, completion on an mbarrier: SYNCS.*) and\n"
        "# written back with UTMASTG.2D + UTMACMDFLUSH (bulk_group commit / wait)",
        os.path.join(B, "mlaa_kernels.cu.o"), os.path.join(B, "mlaa_kernels.cu.o.log"), "vstrip_tma",
        ("UTMA", "SYNCS", "LDS", "STS", "FENCE", "BAR"), r"UTMA|SYNCS|FENCE")
-print("written: profiles/r02_sass_rt_pool_kernel.txt, profiles/r02_sass_mlaa_tma.txt")
+print("written: profiles/r03_sass_rt_pool_kernel.txt, profiles/r03_sass_mlaa_tma.txt")
