@@ -267,11 +267,12 @@ def run_reference_arm(args, wl):
         return
     t0 = time.time()
     raster = bool(wl.get("raster"))
-    # rays per frame: mean over five frames spread over the orbit frames the B200 arm times (warmup .. warmup+steps-1)
+    # rays per frame: mean over the orbit frames the B200 arm times (warmup .. warmup+steps-1) - for C2 the fixture holds every one of
+    # them, so both arms convert fps to Mrays/s with the same count (the restatement's counters equal the device's, tests/)
     K, Wm = max(1, args.steps), args.warmup
-    rays = 0 if raster else fixture_rays_per_frame(args.workload, sorted({Wm + (K - 1) * q // 4 for q in range(5)}))
+    rays = 0 if raster else fixture_rays_per_frame(args.workload, list(range(Wm, Wm + K)))
     # each "step" is a bounded sample: the reference renders a batch of orbit frames; K+W batches in total
-    per_step = max(1.5, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
+    per_step = float(os.environ.get("B200R_REF_STEP_SECONDS", "0")) or max(1.5, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
     vals = []
     runner = RefRunner(wl)
     for i in range(args.warmup + args.steps):
@@ -287,7 +288,11 @@ def run_reference_arm(args, wl):
     line = {"impl": "reference", "metric": unit, "value": val, "unit": unit, "fps": fps, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / fps if fps else None,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "rays_per_frame": rays, "note": "reference CPU arm: no GPU involved"},
+            # (the same keys as the B200 arm's `config`, so the two lines can be laid side by side)
+            "config": {"workload": wl["desc"], "camera": "reference -b orbit, one new frame per step", "rays_per_frame": rays,
+                       "raster_per_frame": None, "l2": "n/a: reference CPU arm, no GPU involved", "frames_in_flight": 1,
+                       "host_enqueue_ms_per_step": None, "parallelism": f"{cb['cores']} host threads (the reference's OpenMP loop)",
+                       "timing": "fps from the reference's own printout (src/renderer.cc:631-633) over a batch of orbit frames per step"},
             "cpu_baseline": cb,
             "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.time() - t0}
