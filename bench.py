@@ -540,6 +540,15 @@ def run_b200_arm(args, wl):
 
     if rank == 0:
         cpu = None
+        roof_main = None
+        if pipe_ms_per_step is not None:
+            roof_main = roofline_of(kern_inflight_ms, f"same run as `value`: CUDA events on each frame's own stream around this rank's kernels of that frame, "
+                                                      f"mean over the K timed frames. Up to {depth} frames are in flight, so a launch shares the SMs with its "
+                                                      "neighbours: kernel_ms is a RESIDENCE time and exceeds ms_per_step by about `concurrency`; `alone` "
+                                                      "(= `serial.roofline`) is the same launch timed by itself in this very invocation")
+            roof_main["concurrency"] = kern_inflight_ms / pipe_ms_per_step          # launches of this rank resident at the same time, on average
+            a_alone = (alg_bytes_mine / K) / (kern_alone_ms / 1000.0) / 1e9
+            roof_main["alone"] = {"kernel_ms": kern_alone_ms, "achieved": a_alone, "frac": a_alone / peak, "unit": "GB/s"}
         if P == 1 and not args.no_cpu_baseline:
             cpu = cpu_reference(wl, target_seconds=15.0, rays_per_frame=rays_total / K)
         in_flight = depth if pipe_ms_per_step is not None else 1
@@ -568,10 +577,7 @@ def run_b200_arm(args, wl):
                                  "CUDA events on the launching stream around every step, max over ranks"},
             # one protocol per object: `roofline` belongs to the run `value` comes from (per-launch durations measured in that very run);
             # `serial` is a first-class object with its own ms_per_step, kernel time and roofline.
-            "roofline": roofline_of(kern_inflight_ms, f"same run as `value`: CUDA events on each frame's own stream around this rank's kernels of that frame, "
-                                                      f"mean over the K timed frames. Up to {in_flight} frames are in flight, so a launch shares the SMs with its "
-                                                      "neighbours: kernel_ms can exceed ms_per_step by up to that factor; `serial.roofline` is the launch timed alone")
-                        if pipe_ms_per_step is not None else
+            "roofline": roof_main if roof_main is not None else
                         roofline_of(kern_alone_ms, "same run as `value`: CUDA events around this rank's kernels of every step"),
             "serial": {"ms_per_step": serial_ms_per_step, "fps": 1000.0 / serial_ms_per_step,
                        "value": (1000.0 / serial_ms_per_step) if raster else rays_total / (serial_ms_per_step * K / 1000.0) / 1e6,
