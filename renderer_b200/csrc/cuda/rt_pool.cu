@@ -23,7 +23,7 @@
 //   * A slot whose pending count reaches zero is resolved: black, or (FUSED) shaded with both outcomes of the light test and
 //     re-armed as the SHADOW ray of its hit, or (generic configurations) appended as a hit record for rt_shade_kernel.
 //     Resolution is deferred until 8 slots wait (or nothing else is left) so the shading code runs with more than one lane.
-//   * Persistent CTAs (3 per SM x 148), 8 independent warps each - no CTA-wide barrier anywhere. Warps pull 8x4-pixel tiles of
+//   * Persistent CTAs of 4 independent warps (24 or 32 warps per SM x 148 SMs) - no CTA-wide barrier anywhere. Warps pull 8x4-pixel tiles of
 //     the screen rectangle that can contain the model (centre-out), build the primary rays themselves and test the root box
 //     against kernel arguments; the frame is cleared beforehand, so the 81 % of C2's pixels that miss are never touched.
 //   * The pool cannot overflow: when it is nearly full the top 32 entries are walked depth-first by their lanes with a private
