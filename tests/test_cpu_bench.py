@@ -159,6 +159,17 @@ def test_b200_arm_assembles_its_line_on_stand_ins(rb, pyport, monkeypatch, capsy
     assert len(dev) == max(5, 2 * bench.DEFAULT_DEPTH) + 10 and not any(e[2] for e in dev)
     assert len(host) == max(5, 2 * bench.DEFAULT_E2E_DEPTH) + 10 and all(e[2] for e in host)
     assert log[-1] == "renderer.close"
+    assert "secondary" not in d                                   # quick runs (--no-cpu-baseline) do not append the rasteriser line
+    # the full default run: CPU reference leg + the rasteriser line from a process of its own, started after the device was released
+    del log[:]
+    monkeypatch.setattr(bench, "cpu_reference", lambda wl, target_seconds=15.0, rays_per_frame=None, runner=None:
+                        {"value": 60.0, "unit": "Mrays/s", "fps": 27.0, "cores": 16, "kind": "reference", "sample": "stand-in"})
+    monkeypatch.setattr(bench, "secondary_line", lambda workload: (log.append(("secondary", workload)), {"metric": "fps", "value": 1900.0})[1])
+    args.no_cpu_baseline = False
+    bench.run_b200_arm(args, bench.WORKLOADS["c2"])
+    d = json.loads([l for l in capsys.readouterr().out.splitlines() if l.startswith("{")][0])
+    assert d["cpu_baseline"]["kind"] == "reference" and d["secondary"] == {"metric": "fps", "value": 1900.0}
+    assert log.index("renderer.close") < log.index(("secondary", "c4")) and log.count("renderer.close") == 1
 
 
 def test_b200_arm_sharded_protocol_on_stand_ins(rb, pyport, monkeypatch, capsys):
@@ -249,3 +260,31 @@ def test_b200_arm_sharded_protocol_on_stand_ins(rb, pyport, monkeypatch, capsys)
     assert [e for e in log if isinstance(e, tuple) and e[0] == "pipeline"] == [("pipeline", 1), ("pipeline", D), ("pipeline", D)]
     assert log.count("uid") == 3 and log[-2:] == ["destroy_pg", "renderer.close"]
     assert sum(1 for e in log if isinstance(e, tuple) and e[0] == "submit" and e[1] == D and e[2]) == max(5, 2 * D) + 10
+
+
+def test_secondary_line_condenses_the_rasteriser_run_and_never_raises(monkeypatch):
+    """The C4 object a default run appends: the child invocation is `bench.py --workload c4 ... --no-secondary` (no recursion), its JSON
+    line (here: the committed one of the final GPU session) is condensed to the headline figures, and any failure becomes
+    {"unavailable": ...} instead of an exception."""
+    import types
+    import bench
+    canned = open(os.path.join(ROOT, "profiles", "r03_bench_c4.json")).read()
+    calls = []
+
+    def fake_run(cmd, **kw):
+        calls.append(cmd)
+        return types.SimpleNamespace(returncode=0, stdout="noise\n" + canned + "\n", stderr="")
+    monkeypatch.setattr(bench.subprocess, "run", fake_run)
+    s = bench.secondary_line("c4")
+    cmd = calls[0]
+    assert cmd[1].endswith("bench.py") and cmd[cmd.index("--workload") + 1] == "c4" and "--no-secondary" in cmd and "--no-cpu-baseline" in cmd
+    full = json.loads(canned)
+    assert s["metric"] == "fps" and s["value"] == full["value"] and s["workload"].startswith("statue.ply 3840x2160 mode 6")
+    assert s["serial"]["fps"] == full["serial"]["fps"] and s["e2e"]["d2h_bytes_per_step"] == 3840 * 2160 * 4 and "clocks" in s
+    monkeypatch.setattr(bench.subprocess, "run", lambda cmd, **kw: types.SimpleNamespace(returncode=3, stdout="", stderr="boom"))
+    assert "exit 3" in bench.secondary_line("c4")["unavailable"]
+
+    def raising(cmd, **kw):
+        raise OSError("no such interpreter")
+    monkeypatch.setattr(bench.subprocess, "run", raising)
+    assert "OSError" in bench.secondary_line("c4")["unavailable"]
