@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""What the hot kernels compile to (run here after a build; writes profiles/r02_sass_*.txt):
+"""What the hot kernels compile to (run here after a build; writes profiles/r03_sass_*.txt):
    registers / stack / spills from the ptxas log, and the SASS instruction mix of the kernel bodies - 128-bit global loads of the
    node / leaf records, shared-memory traffic of the pools, no local loads/stores outside the cold walk_subtree function, the
    TMA instructions of the MLAA strip kernel."""
